@@ -1,0 +1,135 @@
+"""oracle/pyoracle.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end for the two CPU checkers:
+
+* ``kind="port"``  -> oracle/lib/libogjk_oracle_{f32,f64}.so : the C restatement (ogjk_oracle.c)
+* ``kind="ref"``   -> oracle/_ref/libogjk_ref_{f32,f64}.so   : the reference's own CPU sources
+  (GJK/cpu/openGJK.c, GJK/cpu/EPA.c) compiled unmodified by oracle/build_ref.sh
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's cpu_baseline / ``--impl reference`` legs
+may import this module.  The product (opengjk-gpu_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def simplex_dtype(dtype) -> np.dtype:
+    """numpy mirror of gkSimplex (reference GJK/common.h:84-89)."""
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return np.dtype(
+            {
+                "names": ["nvrtx", "vrtx", "vrtx_idx", "witnesses"],
+                "formats": ["<i4", ("<f4", (4, 3)), ("<i4", (4, 2)), ("<f4", (2, 3))],
+                "offsets": [0, 4, 52, 84],
+                "itemsize": 108,
+            }
+        )
+    if dtype == np.float64:
+        return np.dtype(
+            {
+                "names": ["nvrtx", "vrtx", "vrtx_idx", "witnesses"],
+                "formats": ["<i4", ("<f8", (4, 3)), ("<i4", (4, 2)), ("<f8", (2, 3))],
+                "offsets": [0, 8, 104, 136],
+                "itemsize": 184,
+            }
+        )
+    raise TypeError(dtype)
+
+
+def _lib_path(kind: str, dtype: np.dtype) -> str:
+    tag = "f32" if dtype == np.float32 else "f64"
+    if kind == "port":
+        return os.path.join(_HERE, "lib", f"libogjk_oracle_{tag}.so")
+    if kind == "ref":
+        return os.path.join(_HERE, "_ref", f"libogjk_ref_{tag}.so")
+    raise ValueError(kind)
+
+
+def available(kind: str, dtype=np.float32) -> bool:
+    return os.path.exists(_lib_path(kind, np.dtype(dtype)))
+
+
+def _flat(c, off, dtype):
+    """-> (contiguous coords [total,3], offsets int64 or None, uniform nv, n)"""
+    c = np.ascontiguousarray(c, dtype=dtype)
+    if off is None:
+        assert c.ndim == 3 and c.shape[2] == 3, "uniform input must be [n, V, 3]"
+        return c, None, int(c.shape[1]), int(c.shape[0])
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    return c, off, 0, int(off.shape[0] - 1)
+
+
+class Oracle:
+    def __init__(self, kind: str = "port", dtype=np.float32):
+        self.kind = kind
+        self.dtype = np.dtype(dtype)
+        self.sdtype = simplex_dtype(self.dtype)
+        path = _lib_path(kind, self.dtype)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle`")
+        self.lib = ctypes.CDLL(path)
+        self.prefix = "ogjk_oracle_" if kind == "port" else "ogjk_ref_"
+        f = lambda name: getattr(self.lib, self.prefix + name)
+        assert f("sizeof_real")() == self.dtype.itemsize
+        assert f("sizeof_simplex")() == self.sdtype.itemsize
+        self._gjk = f("gjk_batch")
+        self._epa = f("epa_batch")
+        self._idx = f("gjk_epa_indexed")
+        for fn in (self._gjk, self._epa, self._idx):
+            fn.restype = None
+
+    @staticmethod
+    def _p(a):
+        return ctypes.c_void_p(0 if a is None else a.ctypes.data)
+
+    def gjk(self, c1, c2, off1=None, off2=None, nthreads: int = 1, want_iters: bool = False):
+        c1, off1, nv1, n = _flat(c1, off1, self.dtype)
+        c2, off2, nv2, n2 = _flat(c2, off2, self.dtype)
+        assert n == n2
+        simp = np.zeros(n, dtype=self.sdtype)
+        dist = np.zeros(n, dtype=self.dtype)
+        iters = np.zeros(n, dtype=np.int32) if (want_iters and self.kind == "port") else None
+        args = [ctypes.c_long(n), self._p(c1), self._p(off1), ctypes.c_int(nv1), self._p(c2), self._p(off2),
+                ctypes.c_int(nv2), self._p(simp), self._p(dist)]
+        if self.kind == "port":
+            args.append(self._p(iters))
+        args.append(ctypes.c_int(nthreads))
+        self._gjk(*args)
+        return (simp, dist, iters) if want_iters else (simp, dist)
+
+    def epa(self, c1, c2, simplices, distances, off1=None, off2=None, nthreads: int = 1,
+            want_iters: bool = False, normals_init: float = 0.0):
+        """Returns (simplices, distances, normals) -- copies; the inputs are not modified."""
+        c1, off1, nv1, n = _flat(c1, off1, self.dtype)
+        c2, off2, nv2, _ = _flat(c2, off2, self.dtype)
+        simp = np.array(simplices, dtype=self.sdtype, copy=True)
+        dist = np.array(distances, dtype=self.dtype, copy=True)
+        nrm = np.full((n, 3), normals_init, dtype=self.dtype)
+        iters = np.zeros(n, dtype=np.int32) if (want_iters and self.kind == "port") else None
+        args = [ctypes.c_long(n), self._p(c1), self._p(off1), ctypes.c_int(nv1), self._p(c2), self._p(off2),
+                ctypes.c_int(nv2), self._p(simp), self._p(dist), self._p(nrm)]
+        if self.kind == "port":
+            args.append(self._p(iters))
+        args.append(ctypes.c_int(nthreads))
+        self._epa(*args)
+        return (simp, dist, nrm, iters) if want_iters else (simp, dist, nrm)
+
+    def gjk_epa_indexed(self, pool, pairs, off=None, do_gjk=True, do_epa=True, simplices=None,
+                        distances=None, nthreads: int = 1):
+        pool, off, nv, _ = _flat(pool, off, self.dtype)
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32)
+        n = int(pairs.shape[0])
+        simp = np.zeros(n, dtype=self.sdtype) if simplices is None else np.array(simplices, dtype=self.sdtype, copy=True)
+        dist = np.zeros(n, dtype=self.dtype) if distances is None else np.array(distances, dtype=self.dtype, copy=True)
+        nrm = np.zeros((n, 3), dtype=self.dtype)
+        self._idx(ctypes.c_long(n), self._p(pool), self._p(off), ctypes.c_int(nv), self._p(pairs), self._p(simp),
+                  self._p(dist), self._p(nrm), ctypes.c_int(int(do_gjk)), ctypes.c_int(int(do_epa)),
+                  ctypes.c_int(nthreads))
+        return simp, dist, nrm
