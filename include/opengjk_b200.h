@@ -1,0 +1,144 @@
+/*
+ * opengjk_b200.h -- C ABI of the B200-native batched GJK distance / EPA penetration engine.
+ *
+ * This is the drop-in boundary for the reference's GPU path: every function below replaces one host
+ * function of the reference's library layer (GJK/gpu/openGJK.h, implemented at GJK/gpu/openGJK.cu:2787-3311)
+ * and has the same arguments with the same meaning.  Differences, all of them additive:
+ *   - plain C linkage, one symbol set per precision: ogjk_f32_* (reference built with USE_32BITS,
+ *     GJK/common.h:44) and ogjk_f64_* (USE_32BITS commented out).  `OGJK_REAL` below is float / double;
+ *     gkPolytope / gkSimplex / gkCollisionPair arrays are passed as `void*` and must have the reference's
+ *     layouts for that precision (GJK/common.h:68-89; fp32 32/108 B, fp64 48/184 B; pair = 2 x int).
+ *   - every function returns an int status (0 = ok) instead of void; the message of the last failure on the
+ *     calling thread is available from ogjk_last_error().  The reference checks no CUDA call at all.
+ *   - launches go to the stream selected with ogjk_set_stream() (default: the legacy default stream the
+ *     reference uses) and, like the reference (openGJK.cu:2983, 3003, 3141, 3161), each *_device call ends with a
+ *     device synchronisation unless ogjk_set_sync(0) was called.
+ * Semantics kept from the reference: n <= 0 is a silent no-op; simplices[i] on input and bd.s / bd.s_idx are
+ * ignored by GJK; EPA writes the penetration depth as a NEGATIVE distance and leaves pairs with
+ * distance > epsilon untouched except for the contact normal.
+ *
+ * The C++ spellings a user of the reference already calls (compute_minimum_distance(...),
+ * GJK::GPU::computeDistances(...), ...) are inline forwarding wrappers in include/GJK/gpu/openGJK.h and
+ * include/examples/gpu/example.h.
+ */
+#ifndef OPENGJK_B200_H__
+#define OPENGJK_B200_H__
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- process-wide helpers ---------------------------------------------------------------------------- */
+/* Message of the last failed call on this thread ("" if none).  Replaces nothing: the reference has no
+ * error reporting. */
+const char* ogjk_last_error(void);
+/* Library version string, e.g. "opengjk-b200 0.1 (sm_100a)". */
+const char* ogjk_version(void);
+/* Number of CUDA devices visible, or -1 on error. */
+int ogjk_device_count(void);
+/* Select the CUDA device subsequent calls on this thread use (the reference uses the current device). */
+int ogjk_set_device(int device);
+/* Stream (a cudaStream_t cast to void*) used by subsequent launches/copies on this thread; NULL = default. */
+int ogjk_set_stream(void* stream);
+/* 1 (default): *_device calls synchronise the device before returning, as the reference does; 0: async. */
+int ogjk_set_sync(int enabled);
+/* Number of kernels this library has launched on the calling thread since the last reset (bench accounting). */
+long long ogjk_launch_count(int reset);
+
+#define OGJK_DECLARE_API(P, OGJK_REAL)                                                                          \
+  /* ---- high level: host pointers, device memory handled internally -------------------------------- */     \
+  /* reference: compute_minimum_distance, GJK/gpu/openGJK.h:91-97 (openGJK.cu:2791-2819) */                     \
+  int ogjk_##P##_compute_minimum_distance(int n, const void* bd1, const void* bd2, void* simplices,            \
+                                          OGJK_REAL* distances);                                                \
+  /* reference: computeCollisionInformation, openGJK.h:112-119 (openGJK.cu:2821-2852); uploads the caller's   \
+   * simplices AND distances (the reference forgets the latter, SURVEY.md section 7 quirk iv) */               \
+  int ogjk_##P##_compute_collision_information(int n, const void* bd1, const void* bd2, void* simplices,       \
+                                               OGJK_REAL* distances, OGJK_REAL* contact_normals);              \
+  /* reference: compute_gjk_epa, openGJK.h:134-141 (openGJK.cu:2854-2883) */                                    \
+  int ogjk_##P##_compute_gjk_epa(int n, const void* bd1, const void* bd2, void* simplices,                     \
+                                 OGJK_REAL* distances, OGJK_REAL* contact_normals);                            \
+  /* README spelling GJK::GPU::computeCollisionInformation(n, bd1, bd2, simplices, distances, witness1,        \
+   * witness2, contact_normals) (reference README.md:38-47): GJK + EPA, witnesses also copied to n x 3 arrays;  \
+   * witness1 / witness2 / contact_normals may be NULL */                                                       \
+  int ogjk_##P##_compute_collision_information_witness(int n, const void* bd1, const void* bd2,                \
+                                                       void* simplices, OGJK_REAL* distances,                  \
+                                                       OGJK_REAL* witness1, OGJK_REAL* witness2,               \
+                                                       OGJK_REAL* contact_normals);                            \
+  /* ---- mid level: explicit device memory -------------------------------------------------------------- */ \
+  /* reference: allocate_and_copy_device_arrays, openGJK.h:212-222 (openGJK.cu:2889-2954).  d_simplices is     \
+   * zero-filled; descriptors in *d_bd1 / *d_bd2 point into *d_coord1 / *d_coord2 (flattened xyz). */          \
+  int ogjk_##P##_allocate_and_copy_device_arrays(int n, const void* bd1, const void* bd2, void** d_bd1,        \
+                                                 void** d_bd2, OGJK_REAL** d_coord1, OGJK_REAL** d_coord2,     \
+                                                 void** d_simplices, OGJK_REAL** d_distances);                 \
+  /* reference: compute_minimum_distance_device, openGJK.h:237-243 (openGJK.cu:2968-2984) */                    \
+  int ogjk_##P##_compute_minimum_distance_device(int n, const void* d_bd1, const void* d_bd2,                  \
+                                                 void* d_simplices, OGJK_REAL* d_distances);                   \
+  /* reference: compute_epa_device, openGJK.h:255-262 (openGJK.cu:2986-3004) */                                 \
+  int ogjk_##P##_compute_epa_device(int n, const void* d_bd1, const void* d_bd2, void* d_simplices,            \
+                                    OGJK_REAL* d_distances, OGJK_REAL* d_contact_normals);                     \
+  /* reference: copy_results_from_device, openGJK.h:273-279 (openGJK.cu:3006-3015) */                           \
+  int ogjk_##P##_copy_results_from_device(int n, const void* d_simplices, const OGJK_REAL* d_distances,        \
+                                          void* simplices, OGJK_REAL* distances);                              \
+  /* reference: free_device_arrays, openGJK.h:292-299 (openGJK.cu:3034-3048) */                                 \
+  int ogjk_##P##_free_device_arrays(void* d_bd1, void* d_bd2, OGJK_REAL* d_coord1, OGJK_REAL* d_coord2,        \
+                                    void* d_simplices, OGJK_REAL* d_distances);                                \
+  /* reference: allocate_epa_device_arrays / copy_epa_results_from_device / free_epa_device_arrays,            \
+   * openGJK.h:155-194 (openGJK.cu:2956-2966, 3017-3032, 3050-3058) */                                         \
+  int ogjk_##P##_allocate_epa_device_arrays(int n, OGJK_REAL** d_witness1, OGJK_REAL** d_witness2,             \
+                                            OGJK_REAL** d_contact_normals);                                    \
+  int ogjk_##P##_copy_epa_results_from_device(int n, const OGJK_REAL* d_witness1,                              \
+                                              const OGJK_REAL* d_witness2,                                     \
+                                              const OGJK_REAL* d_contact_normals, OGJK_REAL* witness1,         \
+                                              OGJK_REAL* witness2, OGJK_REAL* contact_normals);                \
+  int ogjk_##P##_free_epa_device_arrays(OGJK_REAL* d_witness1, OGJK_REAL* d_witness2,                          \
+                                        OGJK_REAL* d_contact_normals);                                         \
+  /* ---- indexed: one polytope pool + (idx1, idx2) pairs ------------------------------------------------ */ \
+  /* reference: allocate_indexed_device, openGJK.h:330-340 (openGJK.cu:3193-3209); d_contact_normals may be    \
+   * NULL; d_simplices is NOT zero-filled (as in the reference) */                                              \
+  int ogjk_##P##_allocate_indexed_device(int num_polytopes, int max_pairs, const void* polytopes,              \
+                                         void** d_polytopes, OGJK_REAL** d_coords, void** d_pairs,             \
+                                         void** d_simplices, OGJK_REAL** d_distances,                          \
+                                         OGJK_REAL** d_contact_normals);                                       \
+  /* reference: free_indexed_device, openGJK.h:352-359 (openGJK.cu:3211-3225) */                                \
+  int ogjk_##P##_free_indexed_device(void* d_polytopes, OGJK_REAL* d_coords, void* d_pairs,                    \
+                                     void* d_simplices, OGJK_REAL* d_distances,                                \
+                                     OGJK_REAL* d_contact_normals);                                            \
+  /* reference: upload_pairs_device, openGJK.h:368-372 (openGJK.cu:3227-3233) */                                \
+  int ogjk_##P##_upload_pairs_device(int num_pairs, const void* pairs, void* d_pairs);                         \
+  /* reference: compute_minimum_distance_indexed, openGJK.h:398-405 (openGJK.cu:3064-3125) */                   \
+  int ogjk_##P##_compute_minimum_distance_indexed(int num_polytopes, int num_pairs, const void* polytopes,     \
+                                                  const void* pairs, void* simplices, OGJK_REAL* distances);   \
+  /* reference: compute_minimum_distance_indexed_device, openGJK.h:419-425 (openGJK.cu:3127-3142) */            \
+  int ogjk_##P##_compute_minimum_distance_indexed_device(int num_pairs, const void* d_polytopes,               \
+                                                         const void* d_pairs, void* d_simplices,               \
+                                                         OGJK_REAL* d_distances);                              \
+  /* reference: compute_epa_indexed_device, openGJK.h:450-457 (openGJK.cu:3144-3163) */                         \
+  int ogjk_##P##_compute_epa_indexed_device(int num_pairs, const void* d_polytopes, const void* d_pairs,       \
+                                            void* d_simplices, OGJK_REAL* d_distances,                         \
+                                            OGJK_REAL* d_contact_normals);                                     \
+  /* reference: compute_epa_indexed, openGJK.h:473-481 (openGJK.cu:3235-3272) */                                \
+  int ogjk_##P##_compute_epa_indexed(int num_polytopes, int num_pairs, const void* polytopes,                  \
+                                     const void* pairs, void* simplices, OGJK_REAL* distances,                 \
+                                     OGJK_REAL* contact_normals);                                              \
+  /* reference: compute_gjk_epa_indexed, openGJK.h:497-505 (openGJK.cu:3274-3311) */                            \
+  int ogjk_##P##_compute_gjk_epa_indexed(int num_polytopes, int num_pairs, const void* polytopes,              \
+                                         const void* pairs, void* simplices, OGJK_REAL* distances,             \
+                                         OGJK_REAL* contact_normals);                                          \
+  /* ---- flat-array entry points (no descriptors): coords are n x nverts x 3, device resident ---------- */ \
+  /* The same GJK / EPA, for callers (benchmarks, Python, other FFIs) that hold uniform batches as dense       \
+   * arrays; equivalent to building descriptors with numpoints = nverts and coord = base + i*nverts*3. */       \
+  int ogjk_##P##_gjk_uniform_device(int n, int nverts1, const OGJK_REAL* d_coord1, int nverts2,                \
+                                    const OGJK_REAL* d_coord2, void* d_simplices, OGJK_REAL* d_distances);     \
+  int ogjk_##P##_epa_uniform_device(int n, int nverts1, const OGJK_REAL* d_coord1, int nverts2,                \
+                                    const OGJK_REAL* d_coord2, void* d_simplices, OGJK_REAL* d_distances,      \
+                                    OGJK_REAL* d_contact_normals);
+
+OGJK_DECLARE_API(f32, float)
+OGJK_DECLARE_API(f64, double)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENGJK_B200_H__ */

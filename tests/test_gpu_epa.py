@@ -1,0 +1,105 @@
+"""GPU parity: EPA (penetration depth, witnesses, contact normal) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import live_simplex_equal
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+
+
+def _oracle_gjk_epa(oracle_mod, dtype, a, b, kind="port"):
+    orc = oracle_mod.Oracle(kind, dtype)
+    s, d = orc.gjk(a, b)
+    return orc.epa(a, b, s, d)
+
+
+def _compare(dtype, got, want):
+    simp, dist, nrm = got
+    osimp, odist, onrm = want
+    eps = np.finfo(dtype).eps
+    assert np.array_equal(dist <= eps, odist <= eps), "collision verdict differs"
+    rtol = RTOL[np.dtype(dtype)]
+    np.testing.assert_allclose(dist, odist, rtol=rtol, atol=0)
+    np.testing.assert_allclose(nrm, onrm, rtol=rtol, atol=rtol)
+    np.testing.assert_allclose(simp["witnesses"], osimp["witnesses"], rtol=rtol, atol=rtol)
+    assert np.array_equal(dist, odist), "distances not bit-identical"
+    assert np.array_equal(nrm, onrm), "normals not bit-identical"
+    assert live_simplex_equal(simp, osimp), "simplices not bit-identical"
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("nverts,spread", [(32, 1.0), (8, 1.0), (64, 2.0), (200, 1.5), (32, 10.0), (5, 0.5)])
+def test_gjk_then_epa_matches_oracle(pkg, oracle_mod, dtype, nverts, spread):
+    n = 20000 if nverts <= 64 else 3000
+    a, b = pkg.workloads.random_pairs(n, nverts, spread, seed=99, dtype=dtype)
+    eng = pkg.Engine(dtype)
+    bd1, _k1 = pkg.make_polytopes(a)
+    bd2, _k2 = pkg.make_polytopes(b)
+    got = eng.compute_gjk_epa(bd1, bd2)
+    _compare(dtype, got, _oracle_gjk_epa(oracle_mod, dtype, a, b))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_epa_only_from_oracle_gjk(pkg, oracle_mod, dtype):
+    """computeCollisionInformation / GJK::GPU::computeEPA: caller supplies GJK's simplices + distances."""
+    a, b = pkg.workloads.random_pairs(10000, 32, 1.0, seed=5, dtype=dtype)
+    orc = oracle_mod.Oracle("port", dtype)
+    s, d = orc.gjk(a, b)
+    eng = pkg.Engine(dtype)
+    bd1, _k1 = pkg.make_polytopes(a)
+    bd2, _k2 = pkg.make_polytopes(b)
+    got = eng.compute_collision_information(bd1, bd2, s.copy(), d.copy())
+    _compare(dtype, got, orc.epa(a, b, s, d))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_against_compiled_reference(pkg, oracle_mod, dtype):
+    if not oracle_mod.available("ref", dtype):
+        pytest.skip("oracle/_ref not built")
+    a, b = pkg.workloads.random_pairs(10000, 32, 1.0, seed=31, dtype=dtype)
+    eng = pkg.Engine(dtype)
+    bd1, _k1 = pkg.make_polytopes(a)
+    bd2, _k2 = pkg.make_polytopes(b)
+    got = eng.compute_gjk_epa(bd1, bd2)
+    _compare(dtype, got, _oracle_gjk_epa(oracle_mod, dtype, a, b, kind="ref"))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_symmetric_shapes_cubes(pkg, oracle_mod, dtype):
+    """Reference EPATesting cases 1-3 (examples/gpu/example.cu:385-580): cubes shifted 1 / 2 / 5 along x, plus the
+    README rotated cube.  These exercise exact ties in the support and closest-face searches."""
+    W = pkg.workloads
+    base = W.unit_cube(dtype=dtype)
+    a = np.stack([base, base, base, base])
+    b = np.stack([W.unit_cube((1, 0, 0), dtype), W.unit_cube((2, 0, 0), dtype), W.unit_cube((5, 0, 0), dtype),
+                  W.rotated_cube_readme(dtype)])
+    eng = pkg.Engine(dtype)
+    bd1, _k1 = pkg.make_polytopes(a)
+    bd2, _k2 = pkg.make_polytopes(b)
+    got = eng.compute_gjk_epa(bd1, bd2)
+    want = _oracle_gjk_epa(oracle_mod, dtype, a, b)
+    _compare(dtype, got, want)
+    # known answers (SURVEY.md section 4 golden table)
+    assert got[1][0] == -1.0 and tuple(got[2][0]) == (1.0, 0.0, 0.0)
+    assert got[1][2] == 3.0
+    assert abs(got[1][3] + 1.5) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_grid_cubes_and_spheres(pkg, oracle_mod, dtype):
+    """Reference EPATesting cases 6-8: 9600-vertex grid cubes, 1000-point spheres 1 apart."""
+    W = pkg.workloads
+    c1 = W.cube_grid(40, 1.0, (0, 0, 0), dtype)
+    c2 = W.cube_grid(40, 1.0, (1.2, 0.3, 0.1), dtype)
+    s1 = W.sphere_surface(1000, 2.0, (0, 0, 0), 7, dtype)
+    s2 = W.sphere_surface(1000, 2.0, (1, 0, 0), 8, dtype)
+    eng = pkg.Engine(dtype)
+    orc = oracle_mod.Oracle("port", dtype)
+    for a, b in ((c1, c2), (s1, s2)):
+        bd1, _k1 = pkg.make_polytopes(a[None])
+        bd2, _k2 = pkg.make_polytopes(b[None])
+        got = eng.compute_gjk_epa(bd1, bd2)
+        s, d = orc.gjk(a[None], b[None])
+        _compare(dtype, got, orc.epa(a[None], b[None], s, d))
