@@ -219,15 +219,10 @@ OGJK_D int closest_face(const EpaWork<T>& W, int lane, T& dist) {
   return bf == 0x7fffffff ? -1 : bf;
 }
 
+// EPA for one pair, executed by one full warp with its private shared-memory work area.
 template <typename T, typename Source>
-__global__ void __launch_bounds__(EpaConfig<T>::kWarpsPerBlock * 32)
-epa_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
-           T* __restrict__ normals, int n) {
-  __shared__ EpaWork<T> work[EpaConfig<T>::kWarpsPerBlock];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long pair = (long long)blockIdx.x * EpaConfig<T>::kWarpsPerBlock + warp;
-  if (pair >= n) return;
-  EpaWork<T>& W = work[warp];
+OGJK_D void epa_pair(const Source& src, long long pair, EpaWork<T>& W, int lane, SimplexT<T>* __restrict__ simplices,
+                     T* __restrict__ distances, T* __restrict__ normals) {
   SimplexT<T>* sp = simplices + pair;
   T* nrm_out = normals + 3 * (size_t)pair;
   const T eps = Tol<T>::eps();
@@ -534,6 +529,72 @@ epa_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict_
       distances[pair] = -report_d;
     }
   }
+}
+
+// Gate + compaction (EPA.c:369-373): one thread per pair.  Separated pairs (distance > eps) get their contact
+// normal from the GJK witnesses right here; colliding pairs are appended to a device-side queue so that only they
+// occupy warps in epa_queue_kernel.  (The reference spends a full warp and 9.8 KB of shared memory on every
+// pair, colliding or not: openGJK.cu:2729-2755.)
+template <typename T>
+__global__ void __launch_bounds__(256)
+epa_gate_kernel(const SimplexT<T>* __restrict__ simplices, const T* __restrict__ distances, T* __restrict__ normals,
+                int n, int* __restrict__ queue, int* __restrict__ counters) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool collide = false;
+  if (i < n) {
+    if (distances[i] > Tol<T>::eps()) {
+      const SimplexT<T>* sp = simplices + i;
+      const V3<T> w1 = mk<T>(sp->witnesses[0][0], sp->witnesses[0][1], sp->witnesses[0][2]);
+      const V3<T> w2 = mk<T>(sp->witnesses[1][0], sp->witnesses[1][1], sp->witnesses[1][2]);
+      const V3<T> nr = normal_from_witnesses(w1, w2);
+      T* o = normals + 3 * (size_t)i;
+      o[0] = nr.x;
+      o[1] = nr.y;
+      o[2] = nr.z;
+    } else {
+      collide = true;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, collide);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&counters[0], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (collide) queue[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+  }
+}
+
+// Persistent EPA kernel: warps pull colliding pairs from the queue through an atomic ticket, so pairs whose
+// expansion needs 60 iterations do not hold up those that need 3.
+template <typename T, typename Source>
+__global__ void __launch_bounds__(EpaConfig<T>::kWarpsPerBlock * 32)
+epa_queue_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
+                 T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters) {
+  __shared__ EpaWork<T> work[EpaConfig<T>::kWarpsPerBlock];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int count = counters[0];
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(&counters[1], 1);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= count) break;
+    epa_pair<T, Source>(src, (long long)queue[q], work[warp], lane, simplices, distances, normals);
+    __syncwarp();
+  }
+}
+
+// One warp per pair, no compaction (used when every pair is expected to collide, or for tiny batches).
+template <typename T, typename Source>
+__global__ void __launch_bounds__(EpaConfig<T>::kWarpsPerBlock * 32)
+epa_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
+           T* __restrict__ normals, int n) {
+  __shared__ EpaWork<T> work[EpaConfig<T>::kWarpsPerBlock];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pair = (long long)blockIdx.x * EpaConfig<T>::kWarpsPerBlock + warp;
+  if (pair >= n) return;
+  epa_pair<T, Source>(src, pair, work[warp], lane, simplices, distances, normals);
 }
 
 }  // namespace ogjk

@@ -17,6 +17,7 @@
 #include "epa_kernel.cuh"
 #include "gjk_generic.cuh"
 #include "gjk_tables.h"
+#include "gjk_uniform.cuh"
 #include "ogjk_types.h"
 
 using namespace ogjk;
@@ -106,12 +107,91 @@ int launch_gjk_generic(const Source& src, int n, int nv_hint, SimplexT<T>* d_sim
   return finish_launch("gjk kernel");
 }
 
+// Uniform batches (dense [n][V][3] coordinates, V % 4 == 0, 16-byte aligned): register-resident fast kernel.
+// Returns 1 if the batch does not qualify (caller falls back to the general kernel), 0 on success, <0 on error.
+template <typename T, int L, int VPL>
+void launch_uniform_instance(const T* c1, const T* c2, int nv1, int nv2, SimplexT<T>* simp, T* dist, int n,
+                             const uint32_t* tabs) {
+  const int block = 256;
+  const long long threads = (long long)n * L;
+  const unsigned grid = (unsigned)((threads + block - 1) / block);
+  gjk_uniform_kernel<T, L, VPL><<<grid, block, 0, t_stream>>>(c1, c2, nv1, nv2, simp, dist, n, tabs);
+}
+
+template <typename T>
+int launch_gjk_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist) {
+  const int nv = nv1 > nv2 ? nv1 : nv2;
+  const bool aligned = (((uintptr_t)c1 | (uintptr_t)c2) & 15u) == 0 && nv1 % 4 == 0 && nv2 % 4 == 0;
+  if (!aligned || nv > 256) return 1;
+  const uint32_t* tabs = nullptr;
+  if (int rc = device_tables(&tabs)) return rc < 0 ? rc : -1;
+  // measured on B200 (profiles/): the register-resident kernel wins for fp32 with 17..256 vertices; for tiny
+  // polytopes and for fp64 (twice the registers per vertex) the general kernel is faster.
+  if constexpr (sizeof(T) == 4) {
+    if (nv <= 16) return 1;
+    else if (nv <= 32) launch_uniform_instance<T, 4, 8>(c1, c2, nv1, nv2, simp, dist, n, tabs);
+    else if (nv <= 64) launch_uniform_instance<T, 8, 8>(c1, c2, nv1, nv2, simp, dist, n, tabs);
+    else if (nv <= 128) launch_uniform_instance<T, 16, 8>(c1, c2, nv1, nv2, simp, dist, n, tabs);
+    else launch_uniform_instance<T, 32, 8>(c1, c2, nv1, nv2, simp, dist, n, tabs);
+  } else {
+    return 1;
+  }
+  return finish_launch("gjk uniform kernel");
+}
+
+// ---- per-thread, per-device scratch for the EPA work queue (grow-only) --------------------------------------
+struct Scratch {
+  int* ptr = nullptr;
+  size_t ints = 0;
+};
+thread_local Scratch t_scratch[kMaxDevices];
+
+int epa_scratch(size_t ints, int** out) {
+  int dev = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail_msg("device ordinal out of range");
+  Scratch& s = t_scratch[dev];
+  if (s.ints < ints) {
+    if (s.ptr) cudaFree(s.ptr);
+    s.ptr = nullptr;
+    s.ints = 0;
+    OGJK_CK(cudaMalloc(&s.ptr, ints * sizeof(int)));
+    s.ints = ints;
+  }
+  *out = s.ptr;
+  return 0;
+}
+
+// EPA launch: small batches get one warp per pair; large ones go through gate + compaction + a persistent
+// queue kernel so that only colliding pairs occupy warps.
 template <typename T, typename Source>
 int launch_epa(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distances, T* d_normals) {
   if (!d_normals) return fail_msg("contact_normals must not be NULL on the device path");
-  const int warps_per_block = EpaConfig<T>::kWarpsPerBlock;
-  const unsigned grid = (unsigned)(((long long)n + warps_per_block - 1) / warps_per_block);
-  epa_kernel<T, Source><<<grid, warps_per_block * 32, 0, t_stream>>>(src, d_simplices, d_distances, d_normals, n);
+  constexpr int wpb = EpaConfig<T>::kWarpsPerBlock;
+  if (n < 8192) {
+    const unsigned grid = (unsigned)(((long long)n + wpb - 1) / wpb);
+    epa_kernel<T, Source><<<grid, wpb * 32, 0, t_stream>>>(src, d_simplices, d_distances, d_normals, n);
+    return finish_launch("epa kernel");
+  }
+  int* scratch = nullptr;
+  if (int rc = epa_scratch((size_t)n + 2, &scratch)) return rc;
+  int* counters = scratch;  // [0] = queued pairs, [1] = ticket
+  int* queue = scratch + 2;
+  OGJK_CK(cudaMemsetAsync(counters, 0, 2 * sizeof(int), t_stream));
+  epa_gate_kernel<T><<<(unsigned)(((long long)n + 255) / 256), 256, 0, t_stream>>>(d_simplices, d_distances, d_normals, n,
+                                                                            queue, counters);
+  ++t_launches;
+  OGJK_CK(cudaGetLastError());
+  int dev = 0, sms = 0, per_sm = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_queue_kernel<T, Source>, wpb * 32, 0));
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)sms * per_sm;
+  const long long need = ((long long)n + wpb - 1) / wpb;
+  if (grid > need) grid = need;
+  epa_queue_kernel<T, Source><<<(unsigned)grid, wpb * 32, 0, t_stream>>>(src, d_simplices, d_distances, d_normals, queue,
+                                                                        counters);
   return finish_launch("epa kernel");
 }
 
@@ -201,11 +281,159 @@ struct SyncOverride {  // high-level calls copy results back right after the lau
 // ---- high-level implementations ----------------------------------------------------------------------
 enum Stage : int { kGjk = 1, kEpa = 2 };
 
+// ---- cached device buffers + helper streams for the host-pointer fast path -----------------------------------
+// The reference allocates and frees six device buffers on every high-level call (openGJK.cu:2889-2954, 3034-3048).
+// Here they are grow-only per (thread, device) and re-used, so a steady-state call costs no cudaMalloc/cudaFree.
+enum Slot : int { kSlotC1 = 0, kSlotC2, kSlotSimp, kSlotDist, kSlotNrm, kSlotCount };
+struct DevicePool {
+  void* ptr[kSlotCount] = {};
+  size_t cap[kSlotCount] = {};
+  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done;
+};
+thread_local DevicePool t_pool[kMaxDevices];
+
+int pool_get(DevicePool& p, int slot, size_t bytes, void** out) {
+  if (p.cap[slot] < bytes) {
+    if (p.ptr[slot]) cudaFree(p.ptr[slot]);
+    p.ptr[slot] = nullptr;
+    p.cap[slot] = 0;
+    OGJK_CK(cudaMalloc(&p.ptr[slot], bytes));
+    p.cap[slot] = bytes;
+  }
+  *out = p.ptr[slot];
+  return 0;
+}
+int pool_streams(DevicePool& p, size_t chunks) {
+  if (!p.s_copy) {
+    OGJK_CK(cudaStreamCreateWithFlags(&p.s_copy, cudaStreamNonBlocking));
+    OGJK_CK(cudaStreamCreateWithFlags(&p.s_comp, cudaStreamNonBlocking));
+    OGJK_CK(cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
+  }
+  while (p.ev_in.size() < chunks) {
+    cudaEvent_t a, b;
+    OGJK_CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    OGJK_CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    p.ev_in.push_back(a);
+    p.ev_done.push_back(b);
+  }
+  return 0;
+}
+
+// Is the descriptor array a dense uniform batch, i.e. numpoints identical and coord[i] = coord[0] + i*nv*3 ?
+template <typename T>
+bool dense_uniform(int n, const PolytopeT<T>* bd, int* nv_out) {
+  const int nv = bd[0].numpoints;
+  const T* base = bd[0].coord;
+  if (nv < 1 || !base) return false;
+  const size_t stride = (size_t)nv * 3;
+  for (int i = 0; i < n; ++i)
+    if (bd[i].numpoints != nv || bd[i].coord != base + (size_t)i * stride) return false;
+  *nv_out = nv;
+  return true;
+}
+
+struct StreamOverride {  // run the launch helpers on one of the pool's streams
+  cudaStream_t saved;
+  explicit StreamOverride(cudaStream_t s) : saved(t_stream) { t_stream = s; }
+  ~StreamOverride() { t_stream = saved; }
+};
+
+// Host-pointer fast path for dense uniform batches: the caller's coordinate arrays are DMA'd as they are (no host
+// staging copy, no descriptor upload), in chunks, with the kernels of chunk k overlapping the upload of chunk k+1
+// and the download of chunk k-1.  Returns 1 if the batch does not qualify.
+template <typename T>
+int run_pairs_host_dense(int n, const PolytopeT<T>* bd1, const PolytopeT<T>* bd2, SimplexT<T>* simplices,
+                         T* distances, T* normals, int stages) {
+  int nv1 = 0, nv2 = 0;
+  if (!dense_uniform(n, bd1, &nv1) || !dense_uniform(n, bd2, &nv2)) return 1;
+  if (nv1 % 4 || nv2 % 4 || nv1 > 256 || nv2 > 256) return 1;
+  if ((((uintptr_t)bd1[0].coord | (uintptr_t)bd2[0].coord) & 15u) != 0) return 1;
+  int dev = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  DevicePool& P = t_pool[dev];
+  T *d_c1, *d_c2, *d_dist, *d_nrm = nullptr;
+  SimplexT<T>* d_simp;
+  if (int rc = pool_get(P, kSlotC1, (size_t)n * nv1 * 3 * sizeof(T), (void**)&d_c1)) return rc;
+  if (int rc = pool_get(P, kSlotC2, (size_t)n * nv2 * 3 * sizeof(T), (void**)&d_c2)) return rc;
+  if (int rc = pool_get(P, kSlotSimp, (size_t)n * sizeof(SimplexT<T>), (void**)&d_simp)) return rc;
+  if (int rc = pool_get(P, kSlotDist, (size_t)n * sizeof(T), (void**)&d_dist)) return rc;
+  if (stages & kEpa)
+    if (int rc = pool_get(P, kSlotNrm, (size_t)n * 3 * sizeof(T), (void**)&d_nrm)) return rc;
+
+  const size_t pair_bytes = (size_t)(nv1 + nv2) * 3 * sizeof(T);
+  size_t chunk_pairs = (size_t)(24u << 20) / pair_bytes;  // ~24 MB of coordinates per chunk
+  if (chunk_pairs < 8192) chunk_pairs = 8192;
+  const size_t chunks = ((size_t)n + chunk_pairs - 1) / chunk_pairs;
+  if (int rc = pool_streams(P, chunks)) return rc;
+  // order the pool's streams after whatever the caller queued on the selected stream
+  OGJK_CK(cudaEventRecord(P.ev_done[0], t_stream));
+  OGJK_CK(cudaStreamWaitEvent(P.s_copy, P.ev_done[0], 0));
+  OGJK_CK(cudaStreamWaitEvent(P.s_comp, P.ev_done[0], 0));
+  OGJK_CK(cudaStreamWaitEvent(P.s_out, P.ev_done[0], 0));
+
+  const T* h_c1 = bd1[0].coord;
+  const T* h_c2 = bd2[0].coord;
+  SyncOverride nosync;
+  for (size_t k = 0; k < chunks; ++k) {
+    const size_t lo = k * chunk_pairs;
+    const int m = (int)(((size_t)n - lo) < chunk_pairs ? ((size_t)n - lo) : chunk_pairs);
+    OGJK_CK(cudaMemcpyAsync(d_c1 + lo * nv1 * 3, h_c1 + lo * nv1 * 3, (size_t)m * nv1 * 3 * sizeof(T),
+                            cudaMemcpyHostToDevice, P.s_copy));
+    OGJK_CK(cudaMemcpyAsync(d_c2 + lo * nv2 * 3, h_c2 + lo * nv2 * 3, (size_t)m * nv2 * 3 * sizeof(T),
+                            cudaMemcpyHostToDevice, P.s_copy));
+    if (!(stages & kGjk)) {  // EPA only: the caller's GJK results are inputs (examples/gpu/example.cu:104-105)
+      OGJK_CK(cudaMemcpyAsync(d_simp + lo, simplices + lo, (size_t)m * sizeof(SimplexT<T>), cudaMemcpyHostToDevice,
+                              P.s_copy));
+      OGJK_CK(cudaMemcpyAsync(d_dist + lo, distances + lo, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, P.s_copy));
+    }
+    OGJK_CK(cudaEventRecord(P.ev_in[k], P.s_copy));
+    OGJK_CK(cudaStreamWaitEvent(P.s_comp, P.ev_in[k], 0));
+    {
+      StreamOverride on(P.s_comp);
+      if (stages & kGjk) {
+        int rc = launch_gjk_uniform<T>(m, nv1, d_c1 + lo * nv1 * 3, nv2, d_c2 + lo * nv2 * 3, d_simp + lo, d_dist + lo);
+        if (rc > 0) {
+          UniformSource<T> src{d_c1 + lo * nv1 * 3, d_c2 + lo * nv2 * 3, nv1, nv2};
+          rc = launch_gjk_generic<T>(src, m, (nv1 + nv2) / 2, d_simp + lo, d_dist + lo);
+        }
+        if (rc) return rc;
+      }
+      if (stages & kEpa) {
+        OGJK_CK(cudaMemsetAsync(d_nrm + lo * 3, 0, (size_t)m * 3 * sizeof(T), P.s_comp));
+        UniformSource<T> src{d_c1 + lo * nv1 * 3, d_c2 + lo * nv2 * 3, nv1, nv2};
+        if (int rc = launch_epa<T>(src, m, d_simp + lo, d_dist + lo, d_nrm + lo * 3)) return rc;
+      }
+    }
+    OGJK_CK(cudaEventRecord(P.ev_done[k], P.s_comp));
+    OGJK_CK(cudaStreamWaitEvent(P.s_out, P.ev_done[k], 0));
+    OGJK_CK(cudaMemcpyAsync(simplices + lo, d_simp + lo, (size_t)m * sizeof(SimplexT<T>), cudaMemcpyDeviceToHost, P.s_out));
+    OGJK_CK(cudaMemcpyAsync(distances + lo, d_dist + lo, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, P.s_out));
+    if ((stages & kEpa) && normals)
+      OGJK_CK(cudaMemcpyAsync(normals + lo * 3, d_nrm + lo * 3, (size_t)m * 3 * sizeof(T), cudaMemcpyDeviceToHost, P.s_out));
+  }
+  OGJK_CK(cudaStreamSynchronize(P.s_out));
+  OGJK_CK(cudaStreamSynchronize(P.s_comp));
+  return 0;
+}
+
 template <typename T>
 int run_pairs_host(int n, const PolytopeT<T>* bd1, const PolytopeT<T>* bd2, SimplexT<T>* simplices, T* distances,
                    T* normals, T* witness1, T* witness2, int stages) {
   if (n <= 0) return 0;
   if (!bd1 || !bd2 || !simplices || !distances) return fail_msg("null argument");
+  {
+    const int rc = run_pairs_host_dense<T>(n, bd1, bd2, simplices, distances, normals, stages);
+    if (rc <= 0) {
+      if (rc == 0 && (witness1 || witness2))
+        for (int i = 0; i < n; ++i)
+          for (int c = 0; c < 3; ++c) {
+            if (witness1) witness1[3 * (size_t)i + c] = simplices[i].witnesses[0][c];
+            if (witness2) witness2[3 * (size_t)i + c] = simplices[i].witnesses[1][c];
+          }
+      return rc;
+    }
+  }
   Flattened<T> f1, f2;
   SimplexT<T>* d_simp = nullptr;
   T* d_dist = nullptr;
@@ -514,6 +742,9 @@ long long ogjk_launch_count(int reset) {
                                     void* d_simplices, REAL* d_distances) {                                           \
     if (n <= 0) return 0;                                                                                              \
     if (nverts1 < 1 || nverts2 < 1) return fail_msg("polytope with no vertices");                                      \
+    const int fast = launch_gjk_uniform<REAL>(n, nverts1, d_coord1, nverts2, d_coord2,                                 \
+                                              (SimplexT<REAL>*)d_simplices, d_distances);                              \
+    if (fast <= 0) return fast;                                                                                        \
     UniformSource<REAL> src{d_coord1, d_coord2, nverts1, nverts2};                                                     \
     return launch_gjk_generic<REAL>(src, n, (nverts1 + nverts2) / 2, (SimplexT<REAL>*)d_simplices, d_distances);       \
   }                                                                                                                    \

@@ -973,7 +973,7 @@ static inline const real* body_ptr(const real* c, const long* off, int nv, long 
 void ogjk_oracle_gjk_batch(long n, const real* c1, const long* off1, int nv1, const real* c2,
                            const long* off2, int nv2, osimplex* simplices, real* distances, int* iters,
                            int nthreads) {
-#pragma omp parallel for schedule(static) num_threads(nthreads) if (nthreads > 1)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads) if (nthreads > 1)
   for (long i = 0; i < n; ++i) {
     int n1, n2;
     const real* a = body_ptr(c1, off1, nv1, i, &n1);
@@ -985,7 +985,7 @@ void ogjk_oracle_gjk_batch(long n, const real* c1, const long* off1, int nv1, co
 void ogjk_oracle_epa_batch(long n, const real* c1, const long* off1, int nv1, const real* c2,
                            const long* off2, int nv2, osimplex* simplices, real* distances, real* normals,
                            int* iters, int nthreads) {
-#pragma omp parallel for schedule(static) num_threads(nthreads) if (nthreads > 1)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads) if (nthreads > 1)
   for (long i = 0; i < n; ++i) {
     int n1, n2;
     const real* a = body_ptr(c1, off1, nv1, i, &n1);
@@ -998,7 +998,7 @@ void ogjk_oracle_epa_batch(long n, const real* c1, const long* off1, int nv1, co
 void ogjk_oracle_gjk_epa_indexed(long npairs, const real* pool, const long* off, int nv, const int* pairs,
                                  osimplex* simplices, real* distances, real* normals, int do_gjk,
                                  int do_epa, int nthreads) {
-#pragma omp parallel for schedule(static) num_threads(nthreads) if (nthreads > 1)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads) if (nthreads > 1)
   for (long i = 0; i < npairs; ++i) {
     int n1, n2;
     const real* a = body_ptr(pool, off, nv, pairs[2 * i], &n1);

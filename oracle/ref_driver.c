@@ -32,7 +32,7 @@ int ogjk_ref_sizeof_polytope(void) { return (int)sizeof(gkPolytope); }
 void ogjk_ref_gjk_batch(long n, const gkFloat* c1, const long* off1, int nv1,
                         const gkFloat* c2, const long* off2, int nv2,
                         gkSimplex* simplices, gkFloat* distances, int nthreads) {
-#pragma omp parallel for schedule(static) num_threads(nthreads) if (nthreads > 1)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads) if (nthreads > 1)
   for (long i = 0; i < n; ++i) {
     gkPolytope a, b;
     make_body(&a, c1, off1, nv1, i);
@@ -45,7 +45,7 @@ void ogjk_ref_epa_batch(long n, const gkFloat* c1, const long* off1, int nv1,
                         const gkFloat* c2, const long* off2, int nv2,
                         gkSimplex* simplices, gkFloat* distances,
                         gkFloat* normals, int nthreads) {
-#pragma omp parallel for schedule(static) num_threads(nthreads) if (nthreads > 1)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads) if (nthreads > 1)
   for (long i = 0; i < n; ++i) {
     gkPolytope a, b;
     make_body(&a, c1, off1, nv1, i);
@@ -58,7 +58,7 @@ void ogjk_ref_epa_batch(long n, const gkFloat* c1, const long* off1, int nv1,
 void ogjk_ref_gjk_epa_indexed(long npairs, const gkFloat* pool, const long* off, int nv,
                               const int* pairs, gkSimplex* simplices, gkFloat* distances,
                               gkFloat* normals, int do_gjk, int do_epa, int nthreads) {
-#pragma omp parallel for schedule(static) num_threads(nthreads) if (nthreads > 1)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads) if (nthreads > 1)
   for (long i = 0; i < npairs; ++i) {
     gkPolytope a, b;
     make_body(&a, pool, off, nv, pairs[2 * i]);
