@@ -225,10 +225,8 @@ def ours(args, workload):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
 
-    times = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = (float(x) for x in times.cpu())
+    # device time of the slowest rank decides (no data-path collective exists; this MAX is the only reduction)
+    total_ms, e2e_ms = pkg.sharding.max_over_ranks([total_ms, e2e_s * 1e3], device="cuda")
 
     if rank == 0:
         sbytes = eng.sdtype.itemsize

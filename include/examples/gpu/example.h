@@ -1,0 +1,64 @@
+/*
+ * examples/gpu/example.h -- drop-in for the reference's namespace API (reference examples/gpu/example.h:7-96,
+ * implemented at examples/gpu/example.cu:13-119): GJK::GPU::computeDistances / computeEPA / computeGJKAndEPA with
+ * the same signatures, plus the README spelling computeCollisionInformation(..., witness1, witness2,
+ * contact_normals = nullptr) (reference README.md:38-47) that the reference documents but never defines.
+ * As in the reference, timer() brackets only the kernel launches, not allocation or transfers.
+ */
+#ifndef EXAMPLE_H
+#define EXAMPLE_H
+
+#include "../../GJK/gpu/openGJK.h"
+#include "../common/timer.h"
+
+namespace GJK {
+namespace GPU {
+
+inline GJK::Common::PerformanceTimer& timer() {
+  static GJK::Common::PerformanceTimer t;
+  return t;
+}
+
+inline void computeDistances(const int n, const gkPolytope* bd1, const gkPolytope* bd2, gkSimplex* simplices,
+                             gkFloat* distances) {
+  if (n <= 0) return;
+  gkPolytope *d_bd1 = nullptr, *d_bd2 = nullptr;
+  gkFloat *d_coord1 = nullptr, *d_coord2 = nullptr, *d_distances = nullptr;
+  gkSimplex* d_simplices = nullptr;
+  allocate_and_copy_device_arrays(n, bd1, bd2, &d_bd1, &d_bd2, &d_coord1, &d_coord2, &d_simplices, &d_distances);
+  timer().startGpuTimer();
+  compute_minimum_distance_device(n, d_bd1, d_bd2, d_simplices, d_distances);
+  timer().endGpuTimer();
+  copy_results_from_device(n, d_simplices, d_distances, simplices, distances);
+  free_device_arrays(d_bd1, d_bd2, d_coord1, d_coord2, d_simplices, d_distances);
+}
+
+inline void computeEPA(const int n, const gkPolytope* bd1, const gkPolytope* bd2, gkSimplex* simplices,
+                       gkFloat* distances, gkFloat* contact_normals) {
+  if (n <= 0) return;
+  timer().startGpuTimer();
+  ::computeCollisionInformation(n, bd1, bd2, simplices, distances, contact_normals);
+  timer().endGpuTimer();
+}
+
+inline void computeGJKAndEPA(const int n, const gkPolytope* bd1, const gkPolytope* bd2, gkSimplex* simplices,
+                             gkFloat* distances, gkFloat* contact_normals) {
+  if (n <= 0) return;
+  timer().startGpuTimer();
+  ::compute_gjk_epa(n, bd1, bd2, simplices, distances, contact_normals);
+  timer().endGpuTimer();
+}
+
+/* README spelling: GJK + EPA with the witness points also returned as two n x 3 arrays */
+inline void computeCollisionInformation(const int n, const gkPolytope* bd1, const gkPolytope* bd2,
+                                        gkSimplex* simplices, gkFloat* distances, gkFloat* witness1,
+                                        gkFloat* witness2, gkFloat* contact_normals = nullptr) {
+  if (n <= 0) return;
+  OGJK_API(compute_collision_information_witness)(n, bd1, bd2, simplices, distances, witness1, witness2,
+                                                  contact_normals);
+}
+
+}  // namespace GPU
+}  // namespace GJK
+
+#endif /* EXAMPLE_H */

@@ -277,4 +277,4 @@ class Engine:
                    _ptr(d_coord2), _ptr(d_simplices), _ptr(d_distances), _ptr(d_normals))
 
 
-from . import workloads  # noqa: E402,F401
+from . import sharding, workloads  # noqa: E402,F401

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -17,6 +18,7 @@
 #include "epa_kernel.cuh"
 #include "gjk_generic.cuh"
 #include "gjk_tables.h"
+#include "gjk_slots.cuh"
 #include "gjk_uniform.cuh"
 #include "ogjk_types.h"
 
@@ -118,13 +120,66 @@ void launch_uniform_instance(const T* c1, const T* c2, int nv1, int nv2, Simplex
   gjk_uniform_kernel<T, L, VPL><<<grid, block, 0, t_stream>>>(c1, c2, nv1, nv2, simp, dist, n, tabs);
 }
 
+// ---- persistent slot kernel (fp32, both vertex sets of a pair fit one shared-memory slot) ----------------------
+thread_local int* t_ticket[kMaxDevices] = {};
+
+// development override: OGJK_GJK_KERNEL=slots|uniform|generic forces one kernel family (A/B measurements)
+int forced_kernel() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("OGJK_GJK_KERNEL");
+    cached = !e ? 0 : !strcmp(e, "slots") ? 1 : !strcmp(e, "uniform") ? 2 : !strcmp(e, "generic") ? 3 : 0;
+  }
+  return cached;
+}
+
+int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist,
+                     const uint32_t* tabs) {
+  int dev = 0, sms = 0, per_sm = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  if (!t_ticket[dev]) OGJK_CK(cudaMalloc(&t_ticket[dev], sizeof(int)));
+  const size_t smem = (size_t)kSlotThreads * (sizeof(uint64_t) + slot_bytes(nv1, nv2));
+  OGJK_CK(cudaFuncSetAttribute(gjk_slots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_slots_kernel, kSlotThreads, smem));
+  if (per_sm < 1) return fail_msg("slot kernel does not fit on this device");
+  long long grid = (long long)sms * per_sm;
+  const long long need = ((long long)n + kSlotThreads - 1) / kSlotThreads;
+  if (grid > need) grid = need;
+  OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(int), t_stream));
+  gjk_slots_kernel<<<(unsigned)grid, kSlotThreads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, n, tabs, t_ticket[dev]);
+  return finish_launch("gjk slots kernel");
+}
+
+template <typename T>
+int launch_gjk_slots_if(int, int, const T*, int, const T*, SimplexT<T>*, T*, const uint32_t*) {
+  return 1;
+}
+template <>
+int launch_gjk_slots_if<float>(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp,
+                               float* dist, const uint32_t* tabs) {
+  const int force = forced_kernel();
+  if (force > 1) return 1;
+  if (nv1 + nv2 > 144) return 1;
+  // measured on B200 (profiles/r1_gjk_kernels_ab.txt): with <= 32 vertices per body a slot is small enough for >= 8
+  // resident warps per SM and this kernel is 1.25-1.9x faster than the register-resident one; at 64 vertices only 4
+  // warps fit (199 KB of slots per 128 threads) and the two tie, so larger polytopes stay on gjk_uniform_kernel.
+  if (force == 0 && (nv1 + nv2 > 64 || n < 32768)) return 1;
+  return launch_gjk_slots(n, nv1, c1, nv2, c2, simp, dist, tabs);
+}
+
 template <typename T>
 int launch_gjk_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist) {
   const int nv = nv1 > nv2 ? nv1 : nv2;
   const bool aligned = (((uintptr_t)c1 | (uintptr_t)c2) & 15u) == 0 && nv1 % 4 == 0 && nv2 % 4 == 0;
   if (!aligned || nv > 256) return 1;
+  if (forced_kernel() == 3) return 1;
   const uint32_t* tabs = nullptr;
   if (int rc = device_tables(&tabs)) return rc < 0 ? rc : -1;
+  {
+    const int rc = launch_gjk_slots_if<T>(n, nv1, c1, nv2, c2, simp, dist, tabs);
+    if (rc <= 0) return rc;
+  }
   // measured on B200 (profiles/): the register-resident kernel wins for fp32 with 17..256 vertices; for tiny
   // polytopes and for fp64 (twice the registers per vertex) the general kernel is faster.
   if constexpr (sizeof(T) == 4) {
