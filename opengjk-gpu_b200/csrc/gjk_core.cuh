@@ -228,6 +228,89 @@ OGJK_HD bool gjk_advance(GjkState<T>& g, const uint32_t* __restrict__ t2, const 
   return g.S.n == 4 || g.k == 25;
 }
 
+// ---- lane-uniform iteration (persistent slot kernel) --------------------------------------------
+// Same arithmetic as gjk_advance, arranged so that threads holding 2-, 3- and 4-point simplices execute ONE
+// instruction stream: the newest point `a` is always treated as slot 3, the older points stay in slots 0..m-1,
+// all 12 predicate bits of the 4-point index are evaluated (bits that involve absent slots are garbage computed
+// from stale but finite slot contents and are masked or ignored by the table, gjk_tables.h "unified table"), the
+// closest-point division is shared between the line and the plane case (dot(a,e) and dot(m,a) multiply the same
+// operands), and the surviving points are picked out of {slot0, slot1, slot2, a} by the leaf's permutation.
+// In a thread-per-pair warp this replaces three serialised divergent paths by a single one.
+// `tab` = the 16-bit unified table (any address space).
+template <typename T>
+OGJK_HD bool gjk_advance_u(GjkState<T>& g, const uint16_t* __restrict__ tab) {
+  const T eps_rel = Tol<T>::eps_rel();
+  const T eps_tot = Tol<T>::eps_tot();
+  const V3<T> a = vsub(g.sup1, g.sup2);
+  const T vv = norm2(g.v);
+  const T gap = sub_rn(vv, dot(g.v, a));
+  if (gap <= mul_rn(eps_rel, vv) || gap < eps_tot) return true;
+  if (vv < mul_rn(eps_rel, eps_rel)) return true;
+
+  const int m = g.S.n;  // 1..3 older points
+  const V3<T> pp = mk<T>(mul_rn(a.x, a.x), mul_rn(a.y, a.y), mul_rn(a.z, a.z));
+  const V3<T> p0 = g.S.s0.p, p1 = g.S.s1.p, p2 = g.S.s2.p;
+  const V3<T> e0 = vsub(p0, a), e1 = vsub(p1, a), e2 = vsub(p2, a);
+  uint32_t idx = 0;
+  idx |= edge_test(a, pp, p0) ? 1u : 0u;
+  idx |= edge_test(a, pp, p1) ? 2u : 0u;
+  idx |= edge_test(a, pp, p2) ? 4u : 0u;
+  const bool sss = det3(e1, e0, e2) <= T(0);
+  const bool f2 = dot(a, cross(p1, p0)) <= T(0);
+  const bool f1 = dot(a, cross(p0, p2)) <= T(0);
+  const bool f0 = dot(a, cross(p2, p1)) <= T(0);
+  idx |= (f0 != sss) ? 8u : 0u;
+  idx |= (f1 != sss) ? 16u : 0u;
+  idx |= (f2 != sss) ? 32u : 0u;
+  const V3<T> m01 = cross(e0, e1), m02 = cross(e0, e2), m12 = cross(e1, e2);
+  idx |= (dot(a, cross(e0, m01)) < T(0)) ? (1u << 6) : 0u;
+  idx |= (dot(a, cross(e1, m01)) > T(0)) ? (1u << 7) : 0u;
+  idx |= (dot(a, cross(e0, m02)) < T(0)) ? (1u << 8) : 0u;
+  idx |= (dot(a, cross(e2, m02)) > T(0)) ? (1u << 9) : 0u;
+  idx |= (dot(a, cross(e1, m12)) < T(0)) ? (1u << 10) : 0u;
+  idx |= (dot(a, cross(e2, m12)) > T(0)) ? (1u << 11) : 0u;
+  const uint32_t mask = m == 3 ? 0xfffu : (m == 2 ? 0xffu : 0x1u);
+  const uint32_t base = m == 3 ? 0u : (m == 2 ? 4096u : 4352u);
+  const uint32_t leaf = tab[base + (idx & mask)];
+  const uint32_t kind = (leaf >> 10) & 7u;
+  const uint32_t x = (leaf >> 13) & 3u;
+
+  // closest point on the line (a, slot x) or on the plane of face x; one shared division
+  const V3<T> el = selv(x == 0u, e0, selv(x == 1u, e1, e2));
+  const V3<T> ml = selv(x == 0u, m01, selv(x == 1u, m02, m12));
+  const bool plane = kind == 2u;
+  const V3<T> q = selv(plane, ml, el);
+  const T t = div_rn(dot(q, a), dot(q, q));
+  const V3<T> qt = vscale(q, t);
+  V3<T> nv = selv(plane, qt, vsub(a, qt));
+  nv = selv(kind == 0u, a, nv);
+  nv = selv(kind == 3u, mk<T>(T(0), T(0), T(0)), nv);
+  g.v = selv(kind == 4u, g.v, nv);
+
+  SV<T> nw;
+  nw.p = a;
+  nw.i1 = g.idx1;
+  nw.i2 = g.idx2;
+  const T n0 = norm2(p0);
+  const SV<T> o0 = pick4((leaf >> 2) & 3u, g.S.s0, g.S.s1, g.S.s2, nw);
+  const SV<T> o1 = pick4((leaf >> 4) & 3u, g.S.s0, g.S.s1, g.S.s2, nw);
+  const SV<T> o2 = pick4((leaf >> 6) & 3u, g.S.s0, g.S.s1, g.S.s2, nw);
+  g.S.s0 = o0;
+  g.S.s1 = o1;
+  g.S.s2 = o2;
+  g.S.s3 = nw;  // slot 3 is only live when all four points survive (identity permutation)
+  g.S.n = (int)(leaf & 3u) + 1;
+  // running max of |vertex|^2 (see gjk_advance): the initial point is accounted for when it survives the first
+  // iteration; afterwards only the newest point can raise the maximum.
+  if (m == 1 && g.S.n == 2 && n0 > g.norm2_wmax) g.norm2_wmax = n0;
+  if ((leaf >> 15) & 1u) {
+    const T nn = norm2(a);
+    if (nn > g.norm2_wmax) g.norm2_wmax = nn;
+  }
+  if (norm2(g.v) <= mul_rn(mul_rn(eps_tot, eps_tot), g.norm2_wmax)) return true;
+  return g.S.n == 4 || g.k == 25;
+}
+
 // ---- witnesses (openGJK.cu:884-1189) ----------------------------------------------------------
 // Fetch must provide: V3<T> operator()(int body /*0|1*/, int vertex_index) const
 template <typename T, typename Fetch>

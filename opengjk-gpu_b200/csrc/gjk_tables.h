@@ -230,4 +230,40 @@ inline void build_leaf_tables(LeafTables& t) {
   for (uint32_t i = 0; i < 16; ++i) t.t2[i] = encode_leaf(tree_2d_index(i));
 }
 
+// ---- unified 16-bit table (one lookup for 2-, 3- and 4-point simplices) --------------------------------------
+// The lane-uniform iteration (gjk_advance_u, gjk_core.cuh) always treats the newest point `a` as slot 3 and the
+// older points as slots 0..m-1 (m = 1..3), evaluates the 12 predicate bits of the 4-point index (bits that involve
+// absent slots are garbage) and looks the leaf up at  kUnifiedBase[m] + (index & kUnifiedMask[m]):
+//   m = 3 : the 4-point tree, all 12 bits;
+//   m = 2 : the 3-point tree with b = slot 1, c = slot 0: along[1] = bit 1, along[0] = bit 0,
+//           hff2(a,b,c) = bit 7 (pair (1,0)), hff2(a,c,b) = bit 6 (pair (0,1)); bits 2..5 ignored;
+//   m = 1 : the 2-point rule (S1D, openGJK.c:257-268): bit 0 = hff1(a, slot 0).
+// Leaf16 encoding: bits 0..1 vertices kept - 1 | bits 2..9 source slot of output slot j at bits 2+2j |
+//                  bits 10..12 how v is obtained (VK_*) | bits 13..14 X | bit 15 the newest point survives.
+constexpr int kUnifiedSize = 4096 + 256 + 2;
+constexpr int kUnifiedBase1 = 4096 + 256, kUnifiedBase2 = 4096, kUnifiedBase3 = 0;
+
+inline uint16_t encode_leaf16(const LeafSpec& l) {
+  uint32_t e = (uint32_t)(l.nv - 1) & 3u;
+  for (int j = 0; j < 4; ++j) e |= (uint32_t)(l.src[j] & 3) << (2 + 2 * j);
+  e |= (uint32_t)(l.vkind & 7) << 10;
+  e |= (uint32_t)(l.x & 3) << 13;
+  e |= (uint32_t)(l.keeps_a & 1) << 15;
+  return (uint16_t)e;
+}
+
+inline void build_unified_table(uint16_t* t /* [kUnifiedSize] */) {
+  for (uint32_t i = 0; i < 4096; ++i) t[kUnifiedBase3 + i] = encode_leaf16(tree_3d(i));
+  for (uint32_t i = 0; i < 256; ++i) {
+    const int along0 = i & 1, along1 = (i >> 1) & 1, h01 = (i >> 6) & 1, h10 = (i >> 7) & 1;
+    t[kUnifiedBase2 + i] = encode_leaf16(detail::tree_2d(3, 1, 0, along1, along0, h10, h01));
+  }
+  {
+    LeafSpec keep = {2, {0, 3, 0, 0}, VK_LINE, 0, 1};  // both points stay, v = closest point on the segment
+    fill_perm(keep);
+    t[kUnifiedBase1 + 1] = encode_leaf16(keep);
+    t[kUnifiedBase1 + 0] = encode_leaf16(detail::leaf_vertex(3));  // only the new point stays, v = a
+  }
+}
+
 }  // namespace ogjk

@@ -74,6 +74,29 @@ int device_tables(const uint32_t** out) {
   return 0;
 }
 
+// the 16-bit unified table of the lane-uniform iteration (gjk_tables.h), one copy per device
+const uint16_t* g_utab[kMaxDevices] = {};
+int device_unified_table(const uint16_t** out) {
+  int dev = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail_msg("device ordinal out of range");
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  if (!g_utab[dev]) {
+    static uint16_t host_tab[kUnifiedSize];
+    static bool built = false;
+    if (!built) {
+      build_unified_table(host_tab);
+      built = true;
+    }
+    uint16_t* d = nullptr;
+    OGJK_CK(cudaMalloc(&d, sizeof(host_tab)));
+    OGJK_CK(cudaMemcpy(d, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice));
+    g_utab[dev] = d;
+  }
+  *out = g_utab[dev];
+  return 0;
+}
+
 int finish_launch(const char* what) {
   ++t_launches;
   OGJK_CK(cudaGetLastError());
@@ -121,7 +144,7 @@ void launch_uniform_instance(const T* c1, const T* c2, int nv1, int nv2, Simplex
 }
 
 // ---- persistent slot kernel (fp32, both vertex sets of a pair fit one shared-memory slot) ----------------------
-thread_local int* t_ticket[kMaxDevices] = {};
+thread_local unsigned* t_ticket[kMaxDevices] = {};
 
 // development override: OGJK_GJK_KERNEL=slots|uniform|generic forces one kernel family (A/B measurements)
 int forced_kernel() {
@@ -132,13 +155,24 @@ int forced_kernel() {
   }
   return cached;
 }
+// development override: OGJK_SLOTS_PREFETCH=<pairs> sets the L2 prefetch distance of the slot kernel (0 = off)
+unsigned slots_prefetch_ahead() {
+  static long cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("OGJK_SLOTS_PREFETCH");
+    cached = e ? atol(e) : 16384;
+    if (cached < 0) cached = 0;
+  }
+  return (unsigned)cached;
+}
 
-int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist,
-                     const uint32_t* tabs) {
+int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist) {
   int dev = 0, sms = 0, per_sm = 0;
   OGJK_CK(cudaGetDevice(&dev));
-  if (!t_ticket[dev]) OGJK_CK(cudaMalloc(&t_ticket[dev], sizeof(int)));
-  const size_t smem = (size_t)kSlotThreads * (sizeof(uint64_t) + slot_bytes(nv1, nv2));
+  const uint16_t* utab = nullptr;
+  if (int rc = device_unified_table(&utab)) return rc;
+  if (!t_ticket[dev]) OGJK_CK(cudaMalloc(&t_ticket[dev], sizeof(unsigned)));
+  const size_t smem = (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2);
   OGJK_CK(cudaFuncSetAttribute(gjk_slots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_slots_kernel, kSlotThreads, smem));
@@ -146,26 +180,27 @@ int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, 
   long long grid = (long long)sms * per_sm;
   const long long need = ((long long)n + kSlotThreads - 1) / kSlotThreads;
   if (grid > need) grid = need;
-  OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(int), t_stream));
-  gjk_slots_kernel<<<(unsigned)grid, kSlotThreads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, n, tabs, t_ticket[dev]);
+  OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
+  gjk_slots_kernel<<<(unsigned)grid, kSlotThreads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab,
+                                                                     t_ticket[dev], slots_prefetch_ahead(), 0u);
   return finish_launch("gjk slots kernel");
 }
 
 template <typename T>
-int launch_gjk_slots_if(int, int, const T*, int, const T*, SimplexT<T>*, T*, const uint32_t*) {
+int launch_gjk_slots_if(int, int, const T*, int, const T*, SimplexT<T>*, T*) {
   return 1;
 }
 template <>
 int launch_gjk_slots_if<float>(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp,
-                               float* dist, const uint32_t* tabs) {
+                               float* dist) {
   const int force = forced_kernel();
   if (force > 1) return 1;
-  if (nv1 + nv2 > 144) return 1;
+  if ((size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2) > 227u * 1024u) return 1;
   // measured on B200 (profiles/r1_gjk_kernels_ab.txt): with <= 32 vertices per body a slot is small enough for >= 8
   // resident warps per SM and this kernel is 1.25-1.9x faster than the register-resident one; at 64 vertices only 4
   // warps fit (199 KB of slots per 128 threads) and the two tie, so larger polytopes stay on gjk_uniform_kernel.
   if (force == 0 && (nv1 + nv2 > 64 || n < 32768)) return 1;
-  return launch_gjk_slots(n, nv1, c1, nv2, c2, simp, dist, tabs);
+  return launch_gjk_slots(n, nv1, c1, nv2, c2, simp, dist);
 }
 
 template <typename T>
@@ -177,7 +212,7 @@ int launch_gjk_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, Simple
   const uint32_t* tabs = nullptr;
   if (int rc = device_tables(&tabs)) return rc < 0 ? rc : -1;
   {
-    const int rc = launch_gjk_slots_if<T>(n, nv1, c1, nv2, c2, simp, dist, tabs);
+    const int rc = launch_gjk_slots_if<T>(n, nv1, c1, nv2, c2, simp, dist);
     if (rc <= 0) return rc;
   }
   // measured on B200 (profiles/): the register-resident kernel wins for fp32 with 17..256 vertices; for tiny

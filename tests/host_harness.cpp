@@ -52,11 +52,13 @@ static void put(SimplexOut<T>& o, int j, const SV<T>& s, bool live) {
 
 template <typename T>
 static void run(long n, const T* c1, const long* off1, int nv1, const T* c2, const long* off2, int nv2,
-                SimplexOut<T>* out, T* dist, int* iters) {
+                SimplexOut<T>* out, T* dist, int* iters, bool unified = false) {
   static LeafTables tabs;
+  static uint16_t utab[kUnifiedSize];
   static bool built = false;
   if (!built) {
     build_leaf_tables(tabs);
+    build_unified_table(utab);
     built = true;
   }
   for (long i = 0; i < n; ++i) {
@@ -71,7 +73,7 @@ static void run(long n, const T* c1, const long* off1, int nv1, const T* c2, con
       ++g.k;
       support(a, na, vneg(g.v), g.sup1, g.idx1);
       support(b, nb, g.v, g.sup2, g.idx2);
-      stop = gjk_advance(g, tabs.t2, tabs.t3);
+      stop = unified ? gjk_advance_u(g, utab) : gjk_advance(g, tabs.t2, tabs.t3);
     } while (!stop);
     HostFetch<T> f{{a, b}};
     V3<T> w1, w2;
@@ -94,6 +96,15 @@ extern "C" {
 void harness_gjk_f32(long n, const float* c1, const long* off1, int nv1, const float* c2, const long* off2, int nv2,
                      void* simplices, float* dist, int* iters) {
   run<float>(n, c1, off1, nv1, c2, off2, nv2, (SimplexOut<float>*)simplices, dist, iters);
+}
+// lane-uniform iteration of the persistent slot kernel (gjk_advance_u + the unified 16-bit table)
+void harness_gjku_f32(long n, const float* c1, const long* off1, int nv1, const float* c2, const long* off2, int nv2,
+                      void* simplices, float* dist, int* iters) {
+  run<float>(n, c1, off1, nv1, c2, off2, nv2, (SimplexOut<float>*)simplices, dist, iters, true);
+}
+void harness_gjku_f64(long n, const double* c1, const long* off1, int nv1, const double* c2, const long* off2, int nv2,
+                      void* simplices, double* dist, int* iters) {
+  run<double>(n, c1, off1, nv1, c2, off2, nv2, (SimplexOut<double>*)simplices, dist, iters, true);
 }
 void harness_gjk_f64(long n, const double* c1, const long* off1, int nv1, const double* c2, const long* off2, int nv2,
                      void* simplices, double* dist, int* iters) {
