@@ -133,7 +133,12 @@ long long ogjk_launch_count(int reset);
                                     const OGJK_REAL* d_coord2, void* d_simplices, OGJK_REAL* d_distances);     \
   int ogjk_##P##_epa_uniform_device(int n, int nverts1, const OGJK_REAL* d_coord1, int nverts2,                \
                                     const OGJK_REAL* d_coord2, void* d_simplices, OGJK_REAL* d_distances,      \
-                                    OGJK_REAL* d_contact_normals);
+                                    OGJK_REAL* d_contact_normals);                                             \
+  /* GJK followed by EPA in one call (what compute_gjk_epa does after its upload, reference                   \
+   * GJK/gpu/openGJK.cu:2854-2883); lets the library fuse the EPA gate into the GJK kernel. */                 \
+  int ogjk_##P##_gjk_epa_uniform_device(int n, int nverts1, const OGJK_REAL* d_coord1, int nverts2,            \
+                                        const OGJK_REAL* d_coord2, void* d_simplices, OGJK_REAL* d_distances,  \
+                                        OGJK_REAL* d_contact_normals);
 
 OGJK_DECLARE_API(f32, float)
 OGJK_DECLARE_API(f64, double)

@@ -272,6 +272,11 @@ class Engine:
         self._call("gjk_uniform_device", ctypes.c_int(n), ctypes.c_int(nv1), _ptr(d_coord1), ctypes.c_int(nv2),
                    _ptr(d_coord2), _ptr(d_simplices), _ptr(d_distances))
 
+    def gjk_epa_uniform_device(self, n, nv1, d_coord1, nv2, d_coord2, d_simplices, d_distances, d_normals):
+        """GJK then EPA in one call (lets the library fuse the EPA gate into the GJK kernel)."""
+        self._call("gjk_epa_uniform_device", ctypes.c_int(n), ctypes.c_int(nv1), _ptr(d_coord1), ctypes.c_int(nv2),
+                   _ptr(d_coord2), _ptr(d_simplices), _ptr(d_distances), _ptr(d_normals))
+
     def epa_uniform_device(self, n, nv1, d_coord1, nv2, d_coord2, d_simplices, d_distances, d_normals):
         self._call("epa_uniform_device", ctypes.c_int(n), ctypes.c_int(nv1), _ptr(d_coord1), ctypes.c_int(nv2),
                    _ptr(d_coord2), _ptr(d_simplices), _ptr(d_distances), _ptr(d_normals))

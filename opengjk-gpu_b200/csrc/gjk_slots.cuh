@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "epa_kernel.cuh"
 #include "gjk_core.cuh"
 #include "gjk_generic.cuh"
 #include "gjk_tables.h"
@@ -281,6 +282,265 @@ gjk_slots_kernel(const float* __restrict__ coord1, const float* __restrict__ coo
         store_result(simplices + pair, distances + pair, g, w1, w2);
         state = kNeedWork;
       }
+    }
+  }
+}
+
+// =====================================================================================================================
+// Warp-specialised variant (large slots: one warp per scheduler).
+//
+// profiles/r1d_gjk_slots_v2.txt: with 64+64 vertices only 4 warps fit an SM and the self-service kernel above spends
+// 24 % of its time issuing TMA copies (ptxas serialises cp.async.bulk over the lanes: its operands are uniform
+// registers), 5 % polling/initialising and 20 % in the witness + store code at 2 active lanes -- all on the critical
+// path of the only warp its scheduler has.  Here those jobs move to two helper warps that run in the issue slots the
+// compute warps leave idle (issue utilisation is ~30 %):
+//   * compute warps (CW x 32 threads, one slot each): wait for the slot's mbarrier, iterate (scans + lane-uniform
+//     step), and when the pair terminates copy what the witness stage needs (simplex, v, the <= 8 source vertices)
+//     into a record of a shared-memory ring and flag the slot FREE;
+//   * the loader warp polls the slot flags, draws tickets (chunked global atomic) and issues the TMA refills;
+//   * the finisher warp consumes ring records a warp at a time, one record per lane: witnesses, gkSimplex + distance
+//     stores, and -- for the fused GJK+EPA entry points -- the EPA gate (EPA.c:369-373): separated pairs get their
+//     contact normal from the witnesses, colliding ones are appended to the EPA queue.
+// Synchronisation: slot flag FREE/BUSY/EXIT (plain shared words, fences), per-slot mbarrier for TMA completion (the
+// loader's arrive.expect_tx releases its `pair_of` store to the waiting compute thread), ring with a reservation
+// counter (shared atomic), per-record generation flags and a consumer-published head.
+constexpr int kRingRecords = 64;
+constexpr int kRecWords = 49;  // odd stride: lanes writing/reading consecutive records hit distinct banks
+// record layout (words): 0 pair | 1 n | 2..4 v | 5+5k.. slot k: p.xyz, i1, i2 | 25+6k.. slot k: body-1 xyz, body-2 xyz
+enum : unsigned { kSlotFree = 0u, kSlotBusy = 1u, kSlotExit = 2u };
+
+__host__ __device__ constexpr uint32_t ws_fixed_bytes(int cw) {
+  // mbarriers | table | ctrl | pair_of | ring control (16 B) | ready flags | ring
+  return (uint32_t)cw * 32u * 8u + kSlotTableBytes + (uint32_t)cw * 32u * 4u * 2u + 16u + kRingRecords * 4u +
+         ((kRingRecords * kRecWords * 4u + 15u) & ~15u);
+}
+
+OGJK_D unsigned ld_vol(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+OGJK_D void st_vol(unsigned* p, unsigned v) { *reinterpret_cast<volatile unsigned*>(p) = v; }
+
+struct RecordFetch {  // vertex "index" = original simplex slot in bits 30..31 (see the finisher)
+  const float* verts;  // record words 25..48
+  OGJK_D V3<float> operator()(int body, int i) const {
+    const float* c = verts + 6 * ((unsigned)i >> 30) + 3 * body;
+    return mk<float>(c[0], c[1], c[2]);
+  }
+};
+
+template <int CW>
+__global__ void __launch_bounds__((CW + 2) * 32)
+gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ coord2, int nv1, int nv2,
+                    SimplexT<float>* __restrict__ simplices, float* __restrict__ distances, unsigned n,
+                    const uint16_t* __restrict__ utab_g, unsigned* __restrict__ ticket, unsigned zero,
+                    float* __restrict__ normals, int* __restrict__ epa_queue, int* __restrict__ epa_count) {
+  constexpr int kCompute = CW * 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t sbytes = slot_bytes(nv1, nv2);
+  unsigned char* sp = smem_raw;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp);
+  sp += kCompute * 8;
+  uint16_t* utab = reinterpret_cast<uint16_t*>(sp);
+  sp += kSlotTableBytes;
+  unsigned* ctrl = reinterpret_cast<unsigned*>(sp);
+  sp += kCompute * 4;
+  unsigned* pair_of = reinterpret_cast<unsigned*>(sp);
+  sp += kCompute * 4;
+  unsigned* ring_ctl = reinterpret_cast<unsigned*>(sp);  // [0] tail (reserved), [1] head (consumed), [2] exited warps
+  sp += 16;
+  unsigned* ready = reinterpret_cast<unsigned*>(sp);
+  sp += kRingRecords * 4;
+  float* ring = reinterpret_cast<float*>(sp);
+  unsigned char* slots = smem_raw + ws_fixed_bytes(CW);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bytes1 = (uint32_t)nv1 * 12u, bytes2 = (uint32_t)nv2 * 12u;
+
+  for (int i = tid; i < kUnifiedSize / 2; i += (CW + 2) * 32)
+    reinterpret_cast<uint32_t*>(utab)[i] = __ldg(reinterpret_cast<const uint32_t*>(utab_g) + i);
+  if (tid < kCompute) {
+    mbar_init(smem_addr(&bars[tid]), 1);
+    ctrl[tid] = kSlotFree;
+    pair_of[tid] = 0;
+  }
+  if (tid < kRingRecords) ready[tid] = 0;
+  if (tid < 4) ring_ctl[tid] = 0;
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  fence_proxy_async();
+  __syncthreads();
+
+  if (warp < CW) {
+    // ================================================ compute ================================================
+    const float* s1 = reinterpret_cast<const float*>(slots + (size_t)tid * sbytes);
+    const float* s2 = s1 + 3 * nv1;
+    const uint32_t bar = smem_addr(&bars[tid]);
+    enum { kWait = 0, kRun = 1, kExit = 2 };
+    int state = kWait;
+    uint32_t parity = 0;
+    unsigned pair = 0;
+    GjkState<float> g;
+    for (;;) {
+      if (state == kWait) {
+        if (mbar_test_wait(bar, parity)) {
+          parity ^= 1u;
+          pair = ld_vol(&pair_of[tid]);
+          gjk_init(g, mk<float>(s1[0], s1[1], s1[2]), mk<float>(s2[0], s2[1], s2[2]));
+          state = kRun;
+        } else if (ld_vol(&ctrl[tid]) == kSlotExit) {
+          state = kExit;
+        }
+      }
+      if (__all_sync(0xffffffffu, state == kExit)) break;
+      if (!__any_sync(0xffffffffu, state == kRun)) __nanosleep(32);  // start-up / drain: nothing loaded yet
+      bool finished = false;
+      if (state == kRun) {
+        ++g.k;
+        support_slot(s1, nv1, vneg(g.v), zero, g.sup1, g.idx1);
+        support_slot(s2, nv2, g.v, zero, g.sup2, g.idx2);
+        finished = gjk_advance_u(g, utab);
+      }
+      const unsigned fin = __ballot_sync(0xffffffffu, finished);
+      if (fin) {
+        const unsigned cnt = __popc(fin);
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&ring_ctl[0], cnt);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        while ((int)(base + cnt - ld_vol(&ring_ctl[1])) > kRingRecords) __nanosleep(64);  // ring full: wait for space
+        if (finished) {
+          const unsigned idx = base + __popc(fin & ((1u << lane) - 1u));
+          float* rec = ring + (size_t)(idx % kRingRecords) * kRecWords;
+          rec[0] = __uint_as_float(pair);
+          rec[1] = __int_as_float(g.S.n);
+          rec[2] = g.v.x;
+          rec[3] = g.v.y;
+          rec[4] = g.v.z;
+          const SV<float>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const SV<float>& q = *sv[k];
+            rec[5 + 5 * k + 0] = q.p.x;
+            rec[5 + 5 * k + 1] = q.p.y;
+            rec[5 + 5 * k + 2] = q.p.z;
+            rec[5 + 5 * k + 3] = __int_as_float(q.i1);
+            rec[5 + 5 * k + 4] = __int_as_float(q.i2);
+            rec[25 + 6 * k + 0] = s1[3 * q.i1 + 0];
+            rec[25 + 6 * k + 1] = s1[3 * q.i1 + 1];
+            rec[25 + 6 * k + 2] = s1[3 * q.i1 + 2];
+            rec[25 + 6 * k + 3] = s2[3 * q.i2 + 0];
+            rec[25 + 6 * k + 4] = s2[3 * q.i2 + 1];
+            rec[25 + 6 * k + 5] = s2[3 * q.i2 + 2];
+          }
+          __threadfence_block();  // record + this thread's slot reads before the two flags
+          st_vol(&ready[idx % kRingRecords], idx / kRingRecords + 1u);
+          st_vol(&ctrl[tid], kSlotFree);
+          state = kWait;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      atomicAdd(&ring_ctl[2], 1u);
+    }
+  } else if (warp == CW) {
+    // ================================================ loader =================================================
+    unsigned tk_next = 0, tk_end = 0;  // reserved ticket range (warp-uniform)
+    unsigned exited = 0;               // bit j: slot lane + 32 j has been told to exit
+    for (;;) {
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        const int s = lane + 32 * j;
+        const bool want = !((exited >> j) & 1u) && ld_vol(&ctrl[s]) == kSlotFree;
+        const unsigned wm = __ballot_sync(0xffffffffu, want);
+        if (!wm) continue;
+        any = true;
+        const unsigned cnt = __popc(wm), avail = tk_end - tk_next;
+        unsigned nb = 0;
+        if (cnt > avail) {
+          if (lane == 0) nb = atomicAdd(ticket, (unsigned)kTicketChunk);
+          nb = __shfl_sync(0xffffffffu, nb, 0);
+        }
+        if (want) {
+          const unsigned r = __popc(wm & ((1u << lane) - 1u));
+          const unsigned t = r < avail ? tk_next + r : nb + (r - avail);
+          if (t < n) {
+            __threadfence_block();  // the owner's last reads of the slot happened before it flagged FREE
+            pair_of[s] = t;
+            st_vol(&ctrl[s], kSlotBusy);
+            const uint32_t bar = smem_addr(&bars[s]);
+            const uint32_t dst1 = smem_addr(slots + (size_t)s * sbytes), dst2 = dst1 + bytes1;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(bar, bytes1 + bytes2);  // release: pair_of is visible to the waiting thread
+            tma_bulk_load(dst1, coord1 + (size_t)t * nv1 * 3, bytes1, bar);
+            tma_bulk_load(dst2, coord2 + (size_t)t * nv2 * 3, bytes2, bar);
+          } else {
+            st_vol(&ctrl[s], kSlotExit);
+            exited |= 1u << j;
+          }
+        }
+        if (cnt > avail) {
+          tk_next = nb + (cnt - avail);
+          tk_end = nb + kTicketChunk;
+        } else {
+          tk_next += cnt;
+        }
+      }
+      if (__all_sync(0xffffffffu, exited == (1u << CW) - 1u)) break;
+      if (!any) __nanosleep(100);
+    }
+  } else {
+    // ================================================ finisher ===============================================
+    unsigned cur = 0;
+    for (;;) {
+      const unsigned idx = cur + lane;
+      const bool rdy = ld_vol(&ready[idx % kRingRecords]) == idx / kRingRecords + 1u;
+      const unsigned m = __ballot_sync(0xffffffffu, rdy);
+      const int c = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);  // records ready in order from `cur`
+      if (c == 0) {
+        if (ld_vol(&ring_ctl[2]) == (unsigned)CW && ld_vol(&ring_ctl[0]) == cur) break;
+        __nanosleep(100);
+        continue;
+      }
+      __threadfence_block();
+      if (lane < c) {
+        const float* rec = ring + (size_t)(idx % kRingRecords) * kRecWords;
+        const unsigned pair = __float_as_uint(rec[0]);
+        GjkState<float> g;
+        g.S.n = __float_as_int(rec[1]);
+        g.v = mk<float>(rec[2], rec[3], rec[4]);
+        SV<float>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          sv[k]->p = mk<float>(rec[5 + 5 * k], rec[6 + 5 * k], rec[7 + 5 * k]);
+          // tag (bits 30..31): which record vertex this slot came with -- survives the witness stage's slot shuffles
+          sv[k]->i1 = (int)(__float_as_uint(rec[8 + 5 * k]) | ((unsigned)k << 30));
+          sv[k]->i2 = (int)(__float_as_uint(rec[9 + 5 * k]) | ((unsigned)k << 30));
+        }
+        RecordFetch fetch{rec + 25};
+        V3<float> w1, w2;
+        gjk_witnesses(fetch, g.S, w1, w2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          sv[k]->i1 &= 0x3fffffff;
+          sv[k]->i2 &= 0x3fffffff;
+        }
+        store_result(simplices + pair, distances + pair, g, w1, w2);
+        if (normals) {  // fused EPA gate
+          const float dist = sqrt_rn(norm2(g.v));
+          bool collide = !(dist > Tol<float>::eps());
+          if (!collide) {
+            const V3<float> nr = normal_from_witnesses(w1, w2);
+            float* o = normals + 3 * (size_t)pair;
+            o[0] = nr.x;
+            o[1] = nr.y;
+            o[2] = nr.z;
+          } else {
+            epa_queue[atomicAdd(epa_count, 1)] = (int)pair;
+          }
+        }
+      }
+      __syncwarp();
+      __threadfence_block();
+      cur += (unsigned)c;
+      if (lane == 0) st_vol(&ring_ctl[1], cur);
     }
   }
 }

@@ -146,24 +146,17 @@ void launch_uniform_instance(const T* c1, const T* c2, int nv1, int nv2, Simplex
 // ---- persistent slot kernel (fp32, both vertex sets of a pair fit one shared-memory slot) ----------------------
 thread_local unsigned* t_ticket[kMaxDevices] = {};
 
-// development override: OGJK_GJK_KERNEL=slots|uniform|generic forces one kernel family (A/B measurements)
+// development override: OGJK_GJK_KERNEL=slots|slotsws|uniform|generic forces one kernel family (A/B measurements)
 int forced_kernel() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("OGJK_GJK_KERNEL");
-    cached = !e ? 0 : !strcmp(e, "slots") ? 1 : !strcmp(e, "uniform") ? 2 : !strcmp(e, "generic") ? 3 : 0;
-  }
-  return cached;
+  const char* e = getenv("OGJK_GJK_KERNEL");
+  return !e ? 0 : !strcmp(e, "slots") ? 1 : !strcmp(e, "uniform") ? 2 : !strcmp(e, "generic") ? 3 :
+         !strcmp(e, "slotsws") ? 4 : 0;
 }
 // development override: OGJK_SLOTS_PREFETCH=<pairs> sets the L2 prefetch distance of the slot kernel (0 = off)
 unsigned slots_prefetch_ahead() {
-  static long cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("OGJK_SLOTS_PREFETCH");
-    cached = e ? atol(e) : 16384;
-    if (cached < 0) cached = 0;
-  }
-  return (unsigned)cached;
+  const char* e = getenv("OGJK_SLOTS_PREFETCH");
+  const long v = e ? atol(e) : 0;  // measured: no gain, +40 % DRAM reads (profiles/r1d_gjk_slots_v2.txt)
+  return v < 0 ? 0u : (unsigned)v;
 }
 
 int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist) {
@@ -186,6 +179,50 @@ int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, 
   return finish_launch("gjk slots kernel");
 }
 
+// warp-specialised slot kernel; `cw` compute warps (4 or 8).  normals/queue/count non-null = fused EPA gate.
+int ws_compute_warps(int nv1, int nv2) {
+  const size_t slots8 = (size_t)256 * slot_bytes(nv1, nv2), slots4 = (size_t)128 * slot_bytes(nv1, nv2);
+  if (ws_fixed_bytes(8) + slots8 + kSlotPadBytes <= 227u * 1024u) return 8;
+  if (ws_fixed_bytes(4) + slots4 + kSlotPadBytes <= 227u * 1024u) return 4;
+  return 0;
+}
+template <int CW>
+int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp,
+                           float* dist, float* nrm, int* queue, int* count) {
+  int dev = 0, sms = 0, per_sm = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  const uint16_t* utab = nullptr;
+  if (int rc = device_unified_table(&utab)) return rc;
+  if (!t_ticket[dev]) OGJK_CK(cudaMalloc(&t_ticket[dev], sizeof(unsigned)));
+  const size_t smem = (size_t)ws_fixed_bytes(CW) + kSlotPadBytes + (size_t)CW * 32 * slot_bytes(nv1, nv2);
+  constexpr int threads = (CW + 2) * 32;
+  OGJK_CK(cudaFuncSetAttribute(gjk_slots_ws_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_slots_ws_kernel<CW>, threads, smem));
+  if (per_sm < 1) return fail_msg("slot kernel does not fit on this device");
+  long long grid = (long long)sms * per_sm;
+  const long long need = ((long long)n + CW * 32 - 1) / (CW * 32);
+  if (grid > need) grid = need;
+  OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
+  gjk_slots_ws_kernel<CW><<<(unsigned)grid, threads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab,
+                                                                       t_ticket[dev], 0u, nrm, queue, count);
+  return finish_launch("gjk slots (warp-specialised) kernel");
+}
+int launch_gjk_slots_ws(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist,
+                        float* nrm, int* queue, int* count) {
+  const int cw = ws_compute_warps(nv1, nv2);
+  if (cw == 8) return launch_gjk_slots_ws_cw<8>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count);
+  if (cw == 4) return launch_gjk_slots_ws_cw<4>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count);
+  return 1;
+}
+
+// policy: the warp-specialised kernel pays off when slots are so large that few compute warps fit an SM
+bool use_ws_kernel(int nv1, int nv2) {
+  const char* e = getenv("OGJK_WS_MIN_SLOT");  // development override (bytes)
+  const int thr = e ? atoi(e) : 700;
+  return ws_compute_warps(nv1, nv2) != 0 && (int)slot_bytes(nv1, nv2) >= thr;
+}
+
 template <typename T>
 int launch_gjk_slots_if(int, int, const T*, int, const T*, SimplexT<T>*, T*) {
   return 1;
@@ -194,12 +231,11 @@ template <>
 int launch_gjk_slots_if<float>(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp,
                                float* dist) {
   const int force = forced_kernel();
-  if (force > 1) return 1;
+  if (force == 2 || force == 3) return 1;
+  if (force == 4 || (force == 0 && n >= 32768 && use_ws_kernel(nv1, nv2)))
+    return launch_gjk_slots_ws(n, nv1, c1, nv2, c2, simp, dist, nullptr, nullptr, nullptr);
   if ((size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2) > 227u * 1024u) return 1;
-  // measured on B200 (profiles/r1_gjk_kernels_ab.txt): with <= 32 vertices per body a slot is small enough for >= 8
-  // resident warps per SM and this kernel is 1.25-1.9x faster than the register-resident one; at 64 vertices only 4
-  // warps fit (199 KB of slots per 128 threads) and the two tie, so larger polytopes stay on gjk_uniform_kernel.
-  if (force == 0 && (nv1 + nv2 > 64 || n < 32768)) return 1;
+  if (force == 0 && n < 32768) return 1;
   return launch_gjk_slots(n, nv1, c1, nv2, c2, simp, dist);
 }
 
@@ -252,6 +288,24 @@ int epa_scratch(size_t ints, int** out) {
   return 0;
 }
 
+// persistent EPA over a device-side queue of colliding pairs (counters[0] = queued pairs, counters[1] = ticket)
+template <typename T, typename Source>
+int launch_epa_queue(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distances, T* d_normals, const int* queue,
+                     int* counters) {
+  constexpr int wpb = EpaConfig<T>::kWarpsPerBlock;
+  int dev = 0, sms = 0, per_sm = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_queue_kernel<T, Source>, wpb * 32, 0));
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)sms * per_sm;
+  const long long need = ((long long)n + wpb - 1) / wpb;
+  if (grid > need) grid = need;
+  epa_queue_kernel<T, Source><<<(unsigned)grid, wpb * 32, 0, t_stream>>>(src, d_simplices, d_distances, d_normals, queue,
+                                                                        counters);
+  return finish_launch("epa kernel");
+}
+
 // EPA launch: small batches get one warp per pair; large ones go through gate + compaction + a persistent
 // queue kernel so that only colliding pairs occupy warps.
 template <typename T, typename Source>
@@ -272,17 +326,35 @@ int launch_epa(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distance
                                                                             queue, counters);
   ++t_launches;
   OGJK_CK(cudaGetLastError());
-  int dev = 0, sms = 0, per_sm = 0;
-  OGJK_CK(cudaGetDevice(&dev));
-  OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_queue_kernel<T, Source>, wpb * 32, 0));
-  if (per_sm < 1) per_sm = 1;
-  long long grid = (long long)sms * per_sm;
-  const long long need = ((long long)n + wpb - 1) / wpb;
-  if (grid > need) grid = need;
-  epa_queue_kernel<T, Source><<<(unsigned)grid, wpb * 32, 0, t_stream>>>(src, d_simplices, d_distances, d_normals, queue,
-                                                                        counters);
-  return finish_launch("epa kernel");
+  return launch_epa_queue<T, Source>(src, n, d_simplices, d_distances, d_normals, queue, counters);
+}
+
+// GJK then EPA on a dense uniform device batch.  When the warp-specialised slot kernel applies, its finisher warp
+// also does the EPA gate (normals of separated pairs, queue of colliding ones), which saves the gate kernel's pass
+// over distances + witnesses; otherwise the two stages run back to back as in the reference (openGJK.cu:2854-2883).
+template <typename T>
+int launch_gjk_epa_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist, T* nrm) {
+  if (!nrm) return fail_msg("contact_normals must not be NULL on the device path");
+  UniformSource<T> src{c1, c2, nv1, nv2};
+  if constexpr (sizeof(T) == 4) {
+    const bool aligned = (((uintptr_t)c1 | (uintptr_t)c2) & 15u) == 0 && nv1 % 4 == 0 && nv2 % 4 == 0;
+    const int force = forced_kernel();
+    if (aligned && n >= 32768 && (force == 0 || force == 4) && use_ws_kernel(nv1, nv2)) {
+      int* scratch = nullptr;
+      if (int rc = epa_scratch((size_t)n + 2, &scratch)) return rc;
+      OGJK_CK(cudaMemsetAsync(scratch, 0, 2 * sizeof(int), t_stream));
+      const bool sync_saved = t_sync;
+      t_sync = false;  // no need to synchronise between the two stages
+      const int rc = launch_gjk_slots_ws(n, nv1, c1, nv2, c2, simp, dist, nrm, scratch + 2, scratch);
+      t_sync = sync_saved;
+      if (rc) return rc;
+      return launch_epa_queue<T, UniformSource<T>>(src, n, simp, dist, nrm, scratch + 2, scratch);
+    }
+  }
+  int rc = launch_gjk_uniform<T>(n, nv1, c1, nv2, c2, simp, dist);
+  if (rc > 0) rc = launch_gjk_generic<T>(src, n, (nv1 + nv2) / 2, simp, dist);
+  if (rc) return rc;
+  return launch_epa<T>(src, n, simp, dist, nrm);
 }
 
 // numpoints of the first descriptor of a device array (vertex-count hint for lane selection)
@@ -481,7 +553,12 @@ int run_pairs_host_dense(int n, const PolytopeT<T>* bd1, const PolytopeT<T>* bd2
     OGJK_CK(cudaStreamWaitEvent(P.s_comp, P.ev_in[k], 0));
     {
       StreamOverride on(P.s_comp);
-      if (stages & kGjk) {
+      if ((stages & kGjk) && (stages & kEpa)) {
+        OGJK_CK(cudaMemsetAsync(d_nrm + lo * 3, 0, (size_t)m * 3 * sizeof(T), P.s_comp));
+        if (int rc = launch_gjk_epa_uniform<T>(m, nv1, d_c1 + lo * nv1 * 3, nv2, d_c2 + lo * nv2 * 3, d_simp + lo,
+                                               d_dist + lo, d_nrm + lo * 3))
+          return rc;
+      } else if (stages & kGjk) {
         int rc = launch_gjk_uniform<T>(m, nv1, d_c1 + lo * nv1 * 3, nv2, d_c2 + lo * nv2 * 3, d_simp + lo, d_dist + lo);
         if (rc > 0) {
           UniformSource<T> src{d_c1 + lo * nv1 * 3, d_c2 + lo * nv2 * 3, nv1, nv2};
@@ -489,7 +566,7 @@ int run_pairs_host_dense(int n, const PolytopeT<T>* bd1, const PolytopeT<T>* bd2
         }
         if (rc) return rc;
       }
-      if (stages & kEpa) {
+      if ((stages & kEpa) && !(stages & kGjk)) {
         OGJK_CK(cudaMemsetAsync(d_nrm + lo * 3, 0, (size_t)m * 3 * sizeof(T), P.s_comp));
         UniformSource<T> src{d_c1 + lo * nv1 * 3, d_c2 + lo * nv2 * 3, nv1, nv2};
         if (int rc = launch_epa<T>(src, m, d_simp + lo, d_dist + lo, d_nrm + lo * 3)) return rc;
@@ -837,6 +914,14 @@ long long ogjk_launch_count(int reset) {
     if (fast <= 0) return fast;                                                                                        \
     UniformSource<REAL> src{d_coord1, d_coord2, nverts1, nverts2};                                                     \
     return launch_gjk_generic<REAL>(src, n, (nverts1 + nverts2) / 2, (SimplexT<REAL>*)d_simplices, d_distances);       \
+  }                                                                                                                    \
+  int ogjk_##P##_gjk_epa_uniform_device(int n, int nverts1, const REAL* d_coord1, int nverts2,                        \
+                                        const REAL* d_coord2, void* d_simplices, REAL* d_distances,                   \
+                                        REAL* d_contact_normals) {                                                    \
+    if (n <= 0) return 0;                                                                                              \
+    if (nverts1 < 1 || nverts2 < 1) return fail_msg("polytope with no vertices");                                      \
+    return launch_gjk_epa_uniform<REAL>(n, nverts1, d_coord1, nverts2, d_coord2, (SimplexT<REAL>*)d_simplices,         \
+                                        d_distances, d_contact_normals);                                               \
   }                                                                                                                    \
   int ogjk_##P##_epa_uniform_device(int n, int nverts1, const REAL* d_coord1, int nverts2, const REAL* d_coord2,      \
                                     void* d_simplices, REAL* d_distances, REAL* d_contact_normals) {                  \
