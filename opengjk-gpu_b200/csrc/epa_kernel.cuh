@@ -45,6 +45,7 @@ struct EpaWork {
   T fd[kEpaMaxFaces];                                      // plane distances (>= 0)
   uint32_t fv[kEpaMaxFaces];                               // v0 | v1<<8 | v2<<16 | live<<24
   uint16_t edge[kEpaMaxFaces * 3];                         // scratch: directed edges of the dying faces, a<<8|b
+  uint8_t rank2slot[kEpaMaxFaces];                         // scratch: r-th lowest free face slot
 };
 
 template <typename T>
@@ -62,12 +63,18 @@ OGJK_D V3<T> normal_from_witnesses(const V3<T>& w1, const V3<T>& w2) {
   return mk<T>(T(1), T(0), T(0));
 }
 
-// Warp-wide (max value, lowest index) reduction.
-template <typename T>
-OGJK_D void warp_argmax(T& best, int& bi) {
+// Warp-wide (max value, lowest index) reduction.  fp64: xor-butterfly on (value, index).  fp32: two REDUX
+// instructions -- the maximum of an order-preserving integer key (-0 is first folded onto +0, which compare equal as
+// floats), then the minimum index among the lanes that hold it.  Only the index is returned.
+OGJK_D unsigned order_key(float x) {
+  const unsigned b = __float_as_uint(add_rn(x, 0.0f));
+  if (!(x == x)) return 0u;  // NaN never wins a strict '>' comparison
+  return b ^ ((b & 0x80000000u) ? 0xffffffffu : 0x80000000u);
+}
+OGJK_D void warp_argmax(double& best, int& bi) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    const T ov = ShflT<T>::xor_(0xffffffffu, best, o);
+    const double ov = ShflT<double>::xor_(0xffffffffu, best, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > best || (ov == best && oi < bi)) {
       best = ov;
@@ -75,30 +82,70 @@ OGJK_D void warp_argmax(T& best, int& bi) {
     }
   }
 }
+OGJK_D void warp_argmax(float& best, int& bi) {
+  const unsigned key = order_key(best);
+  const unsigned top = __reduce_max_sync(0xffffffffu, key);
+  bi = (int)__reduce_min_sync(0xffffffffu, key == top ? (unsigned)bi : 0x7fffffffu);
+}
+
+// This lane's share of a small body (<= 64 vertices: vertices lane and lane + 32), fetched once per pair so that the
+// 10-60 support searches of an expansion do not go back to L1/L2 for them.
+template <typename T>
+struct LaneVerts {
+  V3<T> p[2];
+  bool cached;
+};
+template <typename T>
+OGJK_D LaneVerts<T> cache_lane_verts(const BodyRef<T>& A, int lane) {
+  LaneVerts<T> r;
+  r.cached = A.n <= 64;
+  r.p[0] = r.p[1] = mk<T>(T(0), T(0), T(0));
+  if (r.cached) {
+    if (lane < A.n) r.p[0] = load3(A.c, lane);
+    if (lane + 32 < A.n) r.p[1] = load3(A.c, lane + 32);
+  }
+  return r;
+}
+// per-lane pass of the support search: max of sign * dot(vertex, d) over this lane's vertices, strict '>' from -1e10
+// in ascending index order
+template <typename T>
+OGJK_D void lane_support(const BodyRef<T>& A, const LaneVerts<T>& L, const V3<T>& d, bool negate, int lane, T& best,
+                         int& bi) {
+  best = (T)-1e10f;
+  bi = 0x7fffffff;
+  if (L.cached) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = lane + 32 * k;
+      T sv = dot(L.p[k].x, L.p[k].y, L.p[k].z, d);
+      if (negate) sv = -sv;
+      if (i < A.n && sv > best) {
+        best = sv;
+        bi = i;
+      }
+    }
+  } else {
+    for (int i = lane; i < A.n; i += 32) {
+      const V3<T> p = load3(A.c, i);
+      T sv = dot(p.x, p.y, p.z, d);
+      if (negate) sv = -sv;
+      if (sv > best) {
+        best = sv;
+        bi = i;
+      }
+    }
+  }
+}
 
 // EPA.c:307-344: Minkowski support from scratch; strict '>' from -1e10 in ascending index order, i.e. the
 // lowest index attaining the maximum.  Returns false if either body has no vertex above -1e10.
 template <typename T>
-OGJK_D bool epa_support(const BodyRef<T>& A, const BodyRef<T>& B, const V3<T>& d, int lane, V3<T>& w, int& i1,
-                        int& i2) {
-  T b1 = (T)-1e10f, b2 = (T)-1e10f;
-  int k1 = 0x7fffffff, k2 = 0x7fffffff;
-  for (int i = lane; i < A.n; i += 32) {
-    const V3<T> p = load3(A.c, i);
-    const T s = dot(p.x, p.y, p.z, d);
-    if (s > b1) {
-      b1 = s;
-      k1 = i;
-    }
-  }
-  for (int i = lane; i < B.n; i += 32) {
-    const V3<T> p = load3(B.c, i);
-    const T s = -dot(p.x, p.y, p.z, d);
-    if (s > b2) {
-      b2 = s;
-      k2 = i;
-    }
-  }
+OGJK_D bool epa_support(const BodyRef<T>& A, const BodyRef<T>& B, const LaneVerts<T>& LA, const LaneVerts<T>& LB,
+                        const V3<T>& d, int lane, V3<T>& w, int& i1, int& i2) {
+  T b1, b2;
+  int k1, k2;
+  lane_support(A, LA, d, false, lane, b1, k1);
+  lane_support(B, LB, d, true, lane, b2, k2);
   warp_argmax(b1, k1);
   warp_argmax(b2, k2);
   if (k1 == 0x7fffffff || k2 == 0x7fffffff) return false;
@@ -191,30 +238,42 @@ OGJK_D uint32_t make_face(EpaWork<T>& W, int f, int a, int b, int c, const V3<T>
   return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | (1u << 24);
 }
 
-// Closest live face: smallest distance >= 0, lowest slot on ties (EPA.c:606-617).  -1 if none.
-template <typename T>
-OGJK_D int closest_face(const EpaWork<T>& W, int lane, T& dist) {
-  T best = (T)1e10f;
-  int bf = 0x7fffffff;
-#pragma unroll
-  for (int j = 0; j < kEpaMaxFaces / 32; ++j) {
-    const int f = lane + 32 * j;
-    const bool live = (W.fv[f] >> 24) != 0;
-    const T d = W.fd[f];
-    if (live && d >= T(0) && d < best) {
-      best = d;
-      bf = f;
-    }
-  }
+// Closest live face among slots [0, 32*nwords): smallest distance >= 0, lowest slot on ties (EPA.c:606-617).
+// -1 if none.
+OGJK_D void warp_argmin_nonneg(double& best, int& bf) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    const T od = ShflT<T>::xor_(0xffffffffu, best, o);
+    const double od = ShflT<double>::xor_(0xffffffffu, best, o);
     const int of = __shfl_xor_sync(0xffffffffu, bf, o);
     if (od < best || (od == best && of < bf)) {
       best = od;
       bf = of;
     }
   }
+}
+OGJK_D void warp_argmin_nonneg(float& best, int& bf) {  // best >= 0 (or -0): raw bits order like the values
+  const unsigned key = __float_as_uint(add_rn(best, 0.0f));
+  const unsigned low = __reduce_min_sync(0xffffffffu, key);
+  bf = (int)__reduce_min_sync(0xffffffffu, key == low ? (unsigned)bf : 0x7fffffffu);
+  best = __shfl_sync(0xffffffffu, best, bf & 31);  // the winner's own value (keeps the sign of a zero distance)
+}
+template <typename T>
+OGJK_D int closest_face(const EpaWork<T>& W, int lane, int nwords, T& dist) {
+  T best = (T)1e10f;
+  int bf = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < kEpaMaxFaces / 32; ++j) {
+    if (j < nwords) {
+      const int f = lane + 32 * j;
+      const bool live = (W.fv[f] >> 24) != 0;
+      const T d = W.fd[f];
+      if (live && d >= T(0) && d < best) {
+        best = d;
+        bf = f;
+      }
+    }
+  }
+  warp_argmin_nonneg(best, bf);
   dist = best;
   return bf == 0x7fffffff ? -1 : bf;
 }
@@ -243,6 +302,7 @@ OGJK_D void epa_pair(const Source& src, long long pair, EpaWork<T>& W, int lane,
 
   BodyRef<T> A, B;
   src.get(pair, A, B);
+  const LaneVerts<T> LA = cache_lane_verts(A, lane), LB = cache_lane_verts(B, lane);
 
   // simplex -> first vertices of the polytope
   const int nv_in = sp->nvrtx;
@@ -297,7 +357,7 @@ OGJK_D void epa_pair(const Source& src, long long pair, EpaWork<T>& W, int lane,
     V3<T> p;
     int i1 = 0, i2 = 0;
     if (nv == 1) {
-      const bool ok = epa_support(A, B, work_vertex(W, 0), lane, p, i1, i2);
+      const bool ok = epa_support(A, B, LA, LB, work_vertex(W, 0), lane, p, i1, i2);
       if (ok && is_new(p)) push(p, i1, i2);
       else { touch_exit(i1, i2); return; }
     }
@@ -308,19 +368,19 @@ OGJK_D void epa_pair(const Source& src, long long pair, EpaWork<T>& W, int lane,
       if (len > eps && fabs_(edge.x) > mul_rn((T)0.9f, len)) axis = mk<T>(T(0), T(1), T(0));
       V3<T> dir = cross(edge, axis);
       if (norm2(dir) < eps) dir = cross(edge, mk<T>(T(0), T(0), T(1)));
-      const bool ok = epa_support(A, B, dir, lane, p, i1, i2);
+      const bool ok = epa_support(A, B, LA, LB, dir, lane, p, i1, i2);
       if (ok && is_new(p)) push(p, i1, i2);
       else { touch_exit(i1, i2); return; }
     }
     if (nv == 3) {
       const V3<T> v0 = work_vertex(W, 0);
       V3<T> dir = cross(vsub(work_vertex(W, 1), v0), vsub(work_vertex(W, 2), v0));
-      bool ok = epa_support(A, B, dir, lane, p, i1, i2);
+      bool ok = epa_support(A, B, LA, LB, dir, lane, p, i1, i2);
       if (ok && is_new(p)) {
         push(p, i1, i2);
       } else {
         dir = vneg(dir);
-        ok = epa_support(A, B, dir, lane, p, i1, i2);
+        ok = epa_support(A, B, LA, LB, dir, lane, p, i1, i2);
         if (ok && is_new(p)) push(p, i1, i2);
         else { touch_exit(i1, i2); return; }
       }
@@ -358,20 +418,24 @@ OGJK_D void epa_pair(const Source& src, long long pair, EpaWork<T>& W, int lane,
   __syncwarp();
 
   // ---- 4. expansion (EPA.c:596-826) -----------------------------------------------------------------------------
+  // New faces always take the lowest free slots (EPA.c:761-775), so live faces stay packed in the low slots: `hi`
+  // (one past the highest slot ever used) bounds every per-face pass to ceil(hi/32) words instead of four.
   const T tol = Tol<T>::eps_tot();
   int iter = 0;
+  int hi = 4;
   bool reported = false;
   int report_face = -1;
   T report_d = T(0);
   while (iter < kEpaMaxIters) {
     ++iter;
+    const int nwords = (hi + 31) >> 5;
     T cd;
-    const int cf = closest_face(W, lane, cd);
+    const int cf = closest_face(W, lane, nwords, cd);
     if (cf < 0) break;
     const V3<T> cn = mk<T>(W.nx[cf], W.ny[cf], W.nz[cf]);
     V3<T> w;
     int i1 = 0, i2 = 0;
-    if (!epa_support(A, B, cn, lane, w, i1, i2)) break;
+    if (!epa_support(A, B, LA, LB, cn, lane, w, i1, i2)) break;
     const T gain = sub_rn(dot(cn, w), cd);
     bool stop = gain < tol;
     if (!stop) {  // duplicate of an existing polytope vertex? (EPA.c:654-665)
@@ -407,47 +471,76 @@ OGJK_D void epa_pair(const Source& src, long long pair, EpaWork<T>& W, int lane,
     int nvis = 0;
 #pragma unroll
     for (int j = 0; j < kEpaMaxFaces / 32; ++j) {
-      const int f = lane + 32 * j;
-      const uint32_t word = W.fv[f];
-      fword[j] = word;
-      bool sees = false;
-      if (word >> 24) {
-        const int a = word & 0xff;
-        const V3<T> diff = vsub(w, work_vertex(W, a));
-        sees = dot(mk<T>(W.nx[f], W.ny[f], W.nz[f]), diff) > eps;
+      vis[j] = 0u;
+      fword[j] = 0u;
+      if (j < nwords) {
+        const int f = lane + 32 * j;
+        const uint32_t word = W.fv[f];
+        fword[j] = word;
+        bool sees = false;
+        if (word >> 24) {
+          const int a = word & 0xff;
+          const V3<T> diff = vsub(w, work_vertex(W, a));
+          sees = dot(mk<T>(W.nx[f], W.ny[f], W.nz[f]), diff) > eps;
+        }
+        vis[j] = __ballot_sync(0xffffffffu, sees);
       }
-      vis[j] = __ballot_sync(0xffffffffu, sees);
     }
 #pragma unroll
     for (int j = 0; j < kEpaMaxFaces / 32; ++j) {
-      if ((vis[j] >> lane) & 1u) {
-        const int rank = nvis + __popc(vis[j] & ((1u << lane) - 1u));
-        const uint32_t word = fword[j];
-        const uint32_t a = word & 0xff, b = (word >> 8) & 0xff, c = (word >> 16) & 0xff;
-        W.edge[3 * rank + 0] = (uint16_t)((a << 8) | b);
-        W.edge[3 * rank + 1] = (uint16_t)((b << 8) | c);
-        W.edge[3 * rank + 2] = (uint16_t)((c << 8) | a);
-        W.fv[lane + 32 * j] = word & 0x00ffffffu;  // retire
+      if (j < nwords) {
+        if ((vis[j] >> lane) & 1u) {
+          const int rank = nvis + __popc(vis[j] & ((1u << lane) - 1u));
+          const uint32_t word = fword[j];
+          const uint32_t a = word & 0xff, b = (word >> 8) & 0xff, c = (word >> 16) & 0xff;
+          W.edge[3 * rank + 0] = (uint16_t)((a << 8) | b);
+          W.edge[3 * rank + 1] = (uint16_t)((b << 8) | c);
+          W.edge[3 * rank + 2] = (uint16_t)((c << 8) | a);
+          fword[j] = word & 0x00ffffffu;
+          W.fv[lane + 32 * j] = fword[j];  // retire
+        }
+        nvis += __popc(vis[j]);
       }
-      nvis += __popc(vis[j]);
+    }
+    const int nedge = 3 * nvis;
+
+    // r-th lowest free slot, for r < nedge: slots at or above `hi` are all free, so looking at [0, hi + nedge)
+    // always finds enough -- unless the 128 slots run out, in which case the remaining edges are dropped (EPA.c:775)
+    int nfree = 0;
+    {
+      const int limit = hi + nedge < kEpaMaxFaces ? hi + nedge : kEpaMaxFaces;
+#pragma unroll
+      for (int j = 0; j < kEpaMaxFaces / 32; ++j) {
+        if (32 * j < limit) {
+          const int f = lane + 32 * j;
+          const bool is_free = (fword[j] >> 24) == 0;  // words at or above nwords were never loaded: 0 = free
+          const uint32_t fm = __ballot_sync(0xffffffffu, is_free);
+          if (is_free) W.rank2slot[nfree + __popc(fm & ((1u << lane) - 1u))] = (uint8_t)f;
+          nfree += __popc(fm);
+        }
+      }
     }
     __syncwarp();
 
-    // free slots after the retirements, as a 128-bit mask in slot order
-    uint32_t freem[kEpaMaxFaces / 32];
-#pragma unroll
-    for (int j = 0; j < kEpaMaxFaces / 32; ++j) freem[j] = __ballot_sync(0xffffffffu, (W.fv[lane + 32 * j] >> 24) == 0);
-
     // horizon = edges that occur exactly once (EPA.c:745-759); each gets the next lowest free slot, in edge
-    // order (EPA.c:761-775); when the slots run out the remaining edges are dropped (EPA.c:775)
-    const int nedge = 3 * nvis;
+    // order (EPA.c:761-775)
     int base_rank = 0;
     bool any_degenerate = false;
     for (int e0 = 0; e0 < nedge; e0 += 32) {
       const int e = e0 + lane;
       bool keep = false;
       uint32_t key = 0;
-      if (e < nedge) {
+      if (nedge <= 32) {
+        // one edge per lane: an edge is on the horizon iff no other lane holds the same undirected edge
+        uint32_t canon = 0xffff0000u | (uint32_t)lane;  // idle lanes: unique dummies
+        if (e < nedge) {
+          key = W.edge[e];
+          const uint32_t x = key >> 8, y = key & 0xff;
+          canon = x < y ? key : ((y << 8) | x);
+        }
+        const unsigned same = __match_any_sync(0xffffffffu, canon);
+        keep = e < nedge && __popc(same) == 1;
+      } else if (e < nedge) {
         key = W.edge[e];
         const uint32_t rev = ((key & 0xff) << 8) | (key >> 8);
         keep = true;
@@ -458,17 +551,9 @@ OGJK_D void epa_pair(const Source& src, long long pair, EpaWork<T>& W, int lane,
       }
       const uint32_t keepm = __ballot_sync(0xffffffffu, keep);
       if (keep) {
-        int q = base_rank + __popc(keepm & ((1u << lane) - 1u));
-        int slot = -1;
-#pragma unroll
-        for (int j = 0; j < kEpaMaxFaces / 32; ++j) {
-          const int cnt = __popc(freem[j]);
-          if (slot < 0) {
-            if (q < cnt) slot = 32 * j + (int)__fns(freem[j], 0, q + 1);
-            else q -= cnt;
-          }
-        }
-        if (slot >= 0) {
+        const int q = base_rank + __popc(keepm & ((1u << lane) - 1u));
+        if (q < nfree) {
+          const int slot = W.rank2slot[q];
           bool degenerate = false;
           const uint32_t word = make_face(W, slot, (int)(key >> 8), (int)(key & 0xff), newv, centroid, degenerate);
           W.fv[slot] = word;
@@ -476,6 +561,13 @@ OGJK_D void epa_pair(const Source& src, long long pair, EpaWork<T>& W, int lane,
         }
       }
       base_rank += __popc(keepm);
+    }
+    {
+      const int used = base_rank < nfree ? base_rank : nfree;
+      if (used > 0) {
+        const int top = (int)W.rank2slot[used - 1] + 1;  // ranks ascend with slots
+        hi = top > hi ? top : hi;
+      }
     }
     __syncwarp();
     // degenerate new faces stay "live" while slots are being handed out and are retired at the next plane
@@ -493,7 +585,7 @@ OGJK_D void epa_pair(const Source& src, long long pair, EpaWork<T>& W, int lane,
   // ---- 5. iteration cap: report the currently closest face (EPA.c:828-863) ----------------------------------
   if (!reported && iter >= kEpaMaxIters) {
     T cd;
-    const int cf = closest_face(W, lane, cd);
+    const int cf = closest_face(W, lane, kEpaMaxFaces / 32, cd);
     if (cf >= 0) {
       reported = true;
       report_face = cf;

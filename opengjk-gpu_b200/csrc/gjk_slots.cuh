@@ -309,9 +309,9 @@ constexpr int kRecWords = 49;  // odd stride: lanes writing/reading consecutive 
 // record layout (words): 0 pair | 1 n | 2..4 v | 5+5k.. slot k: p.xyz, i1, i2 | 25+6k.. slot k: body-1 xyz, body-2 xyz
 enum : unsigned { kSlotFree = 0u, kSlotBusy = 1u, kSlotExit = 2u };
 
-__host__ __device__ constexpr uint32_t ws_fixed_bytes(int cw) {
+__host__ __device__ constexpr uint32_t ws_fixed_bytes(int nslots) {
   // mbarriers | table | ctrl | pair_of | ring control (16 B) | ready flags | ring
-  return (uint32_t)cw * 32u * 8u + kSlotTableBytes + (uint32_t)cw * 32u * 4u * 2u + 16u + kRingRecords * 4u +
+  return (uint32_t)nslots * 8u + kSlotTableBytes + (uint32_t)nslots * 4u * 2u + 16u + kRingRecords * 4u +
          ((kRingRecords * kRecWords * 4u + 15u) & ~15u);
 }
 
@@ -326,36 +326,41 @@ struct RecordFetch {  // vertex "index" = original simplex slot in bits 30..31 (
   }
 };
 
-template <int CW>
+// CW compute warps; LP lanes per pair.  LP = 1: a thread per pair.  LP = 2 (slots so large that only 128 fit an SM):
+// the two lanes of a pair each scan ONE body and exchange the support points with a shuffle, everything else is
+// evaluated redundantly on both -- twice the warps for the same shared memory, so each scheduler has a second warp to
+// issue from while the first waits on a dependency.
+template <int CW, int LP>
 __global__ void __launch_bounds__((CW + 2) * 32)
 gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ coord2, int nv1, int nv2,
                     SimplexT<float>* __restrict__ simplices, float* __restrict__ distances, unsigned n,
                     const uint16_t* __restrict__ utab_g, unsigned* __restrict__ ticket, unsigned zero,
                     float* __restrict__ normals, int* __restrict__ epa_queue, int* __restrict__ epa_count) {
   constexpr int kCompute = CW * 32;
+  constexpr int kSlots = kCompute / LP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t sbytes = slot_bytes(nv1, nv2);
   unsigned char* sp = smem_raw;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sp);
-  sp += kCompute * 8;
+  sp += kSlots * 8;
   uint16_t* utab = reinterpret_cast<uint16_t*>(sp);
   sp += kSlotTableBytes;
   unsigned* ctrl = reinterpret_cast<unsigned*>(sp);
-  sp += kCompute * 4;
+  sp += kSlots * 4;
   unsigned* pair_of = reinterpret_cast<unsigned*>(sp);
-  sp += kCompute * 4;
+  sp += kSlots * 4;
   unsigned* ring_ctl = reinterpret_cast<unsigned*>(sp);  // [0] tail (reserved), [1] head (consumed), [2] exited warps
   sp += 16;
   unsigned* ready = reinterpret_cast<unsigned*>(sp);
   sp += kRingRecords * 4;
   float* ring = reinterpret_cast<float*>(sp);
-  unsigned char* slots = smem_raw + ws_fixed_bytes(CW);
+  unsigned char* slots = smem_raw + ws_fixed_bytes(kSlots);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bytes1 = (uint32_t)nv1 * 12u, bytes2 = (uint32_t)nv2 * 12u;
 
   for (int i = tid; i < kUnifiedSize / 2; i += (CW + 2) * 32)
     reinterpret_cast<uint32_t*>(utab)[i] = __ldg(reinterpret_cast<const uint32_t*>(utab_g) + i);
-  if (tid < kCompute) {
+  if (tid < kSlots) {
     mbar_init(smem_addr(&bars[tid]), 1);
     ctrl[tid] = kSlotFree;
     pair_of[tid] = 0;
@@ -368,9 +373,10 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
 
   if (warp < CW) {
     // ================================================ compute ================================================
-    const float* s1 = reinterpret_cast<const float*>(slots + (size_t)tid * sbytes);
+    const int cslot = tid / LP, half = tid % LP;
+    const float* s1 = reinterpret_cast<const float*>(slots + (size_t)cslot * sbytes);
     const float* s2 = s1 + 3 * nv1;
-    const uint32_t bar = smem_addr(&bars[tid]);
+    const uint32_t bar = smem_addr(&bars[cslot]);
     enum { kWait = 0, kRun = 1, kExit = 2 };
     int state = kWait;
     uint32_t parity = 0;
@@ -380,11 +386,18 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
       if (state == kWait) {
         if (mbar_test_wait(bar, parity)) {
           parity ^= 1u;
-          pair = ld_vol(&pair_of[tid]);
+          pair = ld_vol(&pair_of[cslot]);
           gjk_init(g, mk<float>(s1[0], s1[1], s1[2]), mk<float>(s2[0], s2[1], s2[2]));
           state = kRun;
-        } else if (ld_vol(&ctrl[tid]) == kSlotExit) {
+        } else if (ld_vol(&ctrl[cslot]) == kSlotExit) {
           state = kExit;
+        }
+      }
+      if (LP == 2) {  // both lanes of a pair must agree (they polled the same words, but not atomically)
+        const int other = __shfl_xor_sync(0xffffffffu, state, 1);
+        if (other != state) {  // one saw the barrier flip (or EXIT), the other did not yet: retry next trip
+          if (state == kRun) parity ^= 1u;
+          state = kWait;
         }
       }
       if (__all_sync(0xffffffffu, state == kExit)) break;
@@ -392,44 +405,71 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
       bool finished = false;
       if (state == kRun) {
         ++g.k;
-        support_slot(s1, nv1, vneg(g.v), zero, g.sup1, g.idx1);
-        support_slot(s2, nv2, g.v, zero, g.sup2, g.idx2);
+        if (LP == 1) {
+          support_slot(s1, nv1, vneg(g.v), zero, g.sup1, g.idx1);
+          support_slot(s2, nv2, g.v, zero, g.sup2, g.idx2);
+        } else {
+          // this lane's body: half 0 scans body 1 along -v, half 1 scans body 2 along +v
+          const float* body = half ? s2 : s1;
+          const int nvb = half ? nv2 : nv1;
+          const V3<float> d = half ? g.v : vneg(g.v);
+          V3<float> sup = half ? g.sup2 : g.sup1;
+          int sidx = half ? g.idx2 : g.idx1;
+          support_slot(body, nvb, d, zero, sup, sidx);
+          const float ox = __shfl_xor_sync(0xffffffffu, sup.x, 1), oy = __shfl_xor_sync(0xffffffffu, sup.y, 1),
+                      oz = __shfl_xor_sync(0xffffffffu, sup.z, 1);
+          const int oi = __shfl_xor_sync(0xffffffffu, sidx, 1);
+          const V3<float> osup = mk<float>(ox, oy, oz);
+          g.sup1 = half ? osup : sup;
+          g.sup2 = half ? sup : osup;
+          g.idx1 = half ? oi : sidx;
+          g.idx2 = half ? sidx : oi;
+        }
         finished = gjk_advance_u(g, utab);
       }
-      const unsigned fin = __ballot_sync(0xffffffffu, finished);
+      const unsigned fin = __ballot_sync(0xffffffffu, finished && half == 0);
       if (fin) {
         const unsigned cnt = __popc(fin);
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(&ring_ctl[0], cnt);
         base = __shfl_sync(0xffffffffu, base, 0);
         while ((int)(base + cnt - ld_vol(&ring_ctl[1])) > kRingRecords) __nanosleep(64);  // ring full: wait for space
+        const unsigned idx = base + __popc(fin & ((1u << (lane & ~(LP - 1))) - 1u));
         if (finished) {
-          const unsigned idx = base + __popc(fin & ((1u << lane) - 1u));
           float* rec = ring + (size_t)(idx % kRingRecords) * kRecWords;
-          rec[0] = __uint_as_float(pair);
-          rec[1] = __int_as_float(g.S.n);
-          rec[2] = g.v.x;
-          rec[3] = g.v.y;
-          rec[4] = g.v.z;
+          if (half == 0) {
+            rec[0] = __uint_as_float(pair);
+            rec[1] = __int_as_float(g.S.n);
+            rec[2] = g.v.x;
+            rec[3] = g.v.y;
+            rec[4] = g.v.z;
+          }
           const SV<float>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const SV<float>& q = *sv[k];
-            rec[5 + 5 * k + 0] = q.p.x;
-            rec[5 + 5 * k + 1] = q.p.y;
-            rec[5 + 5 * k + 2] = q.p.z;
-            rec[5 + 5 * k + 3] = __int_as_float(q.i1);
-            rec[5 + 5 * k + 4] = __int_as_float(q.i2);
-            rec[25 + 6 * k + 0] = s1[3 * q.i1 + 0];
-            rec[25 + 6 * k + 1] = s1[3 * q.i1 + 1];
-            rec[25 + 6 * k + 2] = s1[3 * q.i1 + 2];
-            rec[25 + 6 * k + 3] = s2[3 * q.i2 + 0];
-            rec[25 + 6 * k + 4] = s2[3 * q.i2 + 1];
-            rec[25 + 6 * k + 5] = s2[3 * q.i2 + 2];
+            if (LP == 1 || (k >> 1) == half) {  // LP = 2: the two lanes write two simplex slots each
+              const SV<float>& q = *sv[k];
+              rec[5 + 5 * k + 0] = q.p.x;
+              rec[5 + 5 * k + 1] = q.p.y;
+              rec[5 + 5 * k + 2] = q.p.z;
+              rec[5 + 5 * k + 3] = __int_as_float(q.i1);
+              rec[5 + 5 * k + 4] = __int_as_float(q.i2);
+              rec[25 + 6 * k + 0] = s1[3 * q.i1 + 0];
+              rec[25 + 6 * k + 1] = s1[3 * q.i1 + 1];
+              rec[25 + 6 * k + 2] = s1[3 * q.i1 + 2];
+              rec[25 + 6 * k + 3] = s2[3 * q.i2 + 0];
+              rec[25 + 6 * k + 4] = s2[3 * q.i2 + 1];
+              rec[25 + 6 * k + 5] = s2[3 * q.i2 + 2];
+            }
           }
           __threadfence_block();  // record + this thread's slot reads before the two flags
-          st_vol(&ready[idx % kRingRecords], idx / kRingRecords + 1u);
-          st_vol(&ctrl[tid], kSlotFree);
+        }
+        __syncwarp();
+        if (finished) {
+          if (half == 0) {
+            st_vol(&ready[idx % kRingRecords], idx / kRingRecords + 1u);
+            st_vol(&ctrl[cslot], kSlotFree);
+          }
           state = kWait;
         }
       }
@@ -446,7 +486,7 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
     for (;;) {
       bool any = false;
 #pragma unroll
-      for (int j = 0; j < CW; ++j) {
+      for (int j = 0; j < kSlots / 32; ++j) {
         const int s = lane + 32 * j;
         const bool want = !((exited >> j) & 1u) && ld_vol(&ctrl[s]) == kSlotFree;
         const unsigned wm = __ballot_sync(0xffffffffu, want);
@@ -483,7 +523,7 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
           tk_next += cnt;
         }
       }
-      if (__all_sync(0xffffffffu, exited == (1u << CW) - 1u)) break;
+      if (__all_sync(0xffffffffu, exited == (1u << (kSlots / 32)) - 1u)) break;
       if (!any) __nanosleep(100);
     }
   } else {

@@ -179,14 +179,25 @@ int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, 
   return finish_launch("gjk slots kernel");
 }
 
-// warp-specialised slot kernel; `cw` compute warps (4 or 8).  normals/queue/count non-null = fused EPA gate.
-int ws_compute_warps(int nv1, int nv2) {
-  const size_t slots8 = (size_t)256 * slot_bytes(nv1, nv2), slots4 = (size_t)128 * slot_bytes(nv1, nv2);
-  if (ws_fixed_bytes(8) + slots8 + kSlotPadBytes <= 227u * 1024u) return 8;
-  if (ws_fixed_bytes(4) + slots4 + kSlotPadBytes <= 227u * 1024u) return 4;
+// warp-specialised slot kernel.  Configurations (compute warps, lanes per pair): (8,1) when 256 slots fit an SM;
+// otherwise (8,2) -- 128 slots, two lanes per pair -- or (4,1).  normals/queue/count non-null = fused EPA gate.
+// development override: OGJK_WS_LP=1|2 picks between (4,1) and (8,2) for the 128-slot case.
+int ws_config(int nv1, int nv2, int* lp) {
+  const size_t sb = slot_bytes(nv1, nv2);
+  *lp = 1;
+  if (ws_fixed_bytes(256) + 256 * sb + kSlotPadBytes <= 227u * 1024u) return 8;
+  if (ws_fixed_bytes(128) + 128 * sb + kSlotPadBytes <= 227u * 1024u) {
+    const char* e = getenv("OGJK_WS_LP");
+    *lp = e ? atoi(e) : 2;
+    return *lp == 2 ? 8 : 4;
+  }
   return 0;
 }
-template <int CW>
+int ws_compute_warps(int nv1, int nv2) {
+  int lp;
+  return ws_config(nv1, nv2, &lp);
+}
+template <int CW, int LP>
 int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp,
                            float* dist, float* nrm, int* queue, int* count) {
   int dev = 0, sms = 0, per_sm = 0;
@@ -194,25 +205,28 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float
   const uint16_t* utab = nullptr;
   if (int rc = device_unified_table(&utab)) return rc;
   if (!t_ticket[dev]) OGJK_CK(cudaMalloc(&t_ticket[dev], sizeof(unsigned)));
-  const size_t smem = (size_t)ws_fixed_bytes(CW) + kSlotPadBytes + (size_t)CW * 32 * slot_bytes(nv1, nv2);
+  constexpr int nslots = CW * 32 / LP;
+  const size_t smem = (size_t)ws_fixed_bytes(nslots) + kSlotPadBytes + (size_t)nslots * slot_bytes(nv1, nv2);
   constexpr int threads = (CW + 2) * 32;
-  OGJK_CK(cudaFuncSetAttribute(gjk_slots_ws_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OGJK_CK(cudaFuncSetAttribute(gjk_slots_ws_kernel<CW, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_slots_ws_kernel<CW>, threads, smem));
+  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_slots_ws_kernel<CW, LP>, threads, smem));
   if (per_sm < 1) return fail_msg("slot kernel does not fit on this device");
   long long grid = (long long)sms * per_sm;
-  const long long need = ((long long)n + CW * 32 - 1) / (CW * 32);
+  const long long need = ((long long)n + nslots - 1) / nslots;
   if (grid > need) grid = need;
   OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
-  gjk_slots_ws_kernel<CW><<<(unsigned)grid, threads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab,
-                                                                       t_ticket[dev], 0u, nrm, queue, count);
+  gjk_slots_ws_kernel<CW, LP><<<(unsigned)grid, threads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n,
+                                                                           utab, t_ticket[dev], 0u, nrm, queue, count);
   return finish_launch("gjk slots (warp-specialised) kernel");
 }
 int launch_gjk_slots_ws(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist,
                         float* nrm, int* queue, int* count) {
-  const int cw = ws_compute_warps(nv1, nv2);
-  if (cw == 8) return launch_gjk_slots_ws_cw<8>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count);
-  if (cw == 4) return launch_gjk_slots_ws_cw<4>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count);
+  int lp = 1;
+  const int cw = ws_config(nv1, nv2, &lp);
+  if (cw == 8 && lp == 1) return launch_gjk_slots_ws_cw<8, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count);
+  if (cw == 8 && lp == 2) return launch_gjk_slots_ws_cw<8, 2>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count);
+  if (cw == 4) return launch_gjk_slots_ws_cw<4, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count);
   return 1;
 }
 
