@@ -286,6 +286,29 @@ gjk_slots_kernel(const float* __restrict__ coord1, const float* __restrict__ coo
   }
 }
 
+// Slot layout of the warp-specialised kernel.  One lane per pair: body 2 follows body 1, odd 16-byte stride (as above).
+// Two lanes per pair: lanes 2p / 2p+1 read body 1 / body 2 of slot p at the same time, so a quarter warp touches four
+// slots x two bodies; with body 2 at an ODD 16-byte offset and a stride that is 2 (mod 4) in 16-byte units the eight
+// 128-bit loads fall into eight different bank groups.
+struct SlotLayout {
+  uint32_t stride, body2;  // bytes
+};
+__host__ __device__ inline SlotLayout ws_slot_layout(int nv1, int nv2, int lp) {
+  SlotLayout L;
+  if (lp == 1) {
+    L.stride = slot_bytes(nv1, nv2);
+    L.body2 = (uint32_t)nv1 * 12u;
+  } else {
+    uint32_t u1 = ((uint32_t)nv1 * 12u + 15u) / 16u;
+    if ((u1 & 1u) == 0) u1 += 1;
+    uint32_t u = u1 + ((uint32_t)nv2 * 12u + 15u) / 16u;
+    while ((u & 3u) != 2u) ++u;
+    L.stride = u * 16u;
+    L.body2 = u1 * 16u;
+  }
+  return L;
+}
+
 // =====================================================================================================================
 // Warp-specialised variant (large slots: one warp per scheduler).
 //
@@ -339,7 +362,8 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
   constexpr int kCompute = CW * 32;
   constexpr int kSlots = kCompute / LP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t sbytes = slot_bytes(nv1, nv2);
+  const SlotLayout lay = ws_slot_layout(nv1, nv2, LP);
+  const uint32_t sbytes = lay.stride;
   unsigned char* sp = smem_raw;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sp);
   sp += kSlots * 8;
@@ -375,7 +399,7 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
     // ================================================ compute ================================================
     const int cslot = tid / LP, half = tid % LP;
     const float* s1 = reinterpret_cast<const float*>(slots + (size_t)cslot * sbytes);
-    const float* s2 = s1 + 3 * nv1;
+    const float* s2 = reinterpret_cast<const float*>(slots + (size_t)cslot * sbytes + lay.body2);
     const uint32_t bar = smem_addr(&bars[cslot]);
     enum { kWait = 0, kRun = 1, kExit = 2 };
     int state = kWait;
@@ -403,6 +427,7 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
       if (__all_sync(0xffffffffu, state == kExit)) break;
       if (!__any_sync(0xffffffffu, state == kRun)) __nanosleep(32);  // start-up / drain: nothing loaded yet
       bool finished = false;
+      const unsigned runm = __ballot_sync(0xffffffffu, state == kRun);  // both lanes of a pair are in it, or neither
       if (state == kRun) {
         ++g.k;
         if (LP == 1) {
@@ -416,9 +441,9 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
           V3<float> sup = half ? g.sup2 : g.sup1;
           int sidx = half ? g.idx2 : g.idx1;
           support_slot(body, nvb, d, zero, sup, sidx);
-          const float ox = __shfl_xor_sync(0xffffffffu, sup.x, 1), oy = __shfl_xor_sync(0xffffffffu, sup.y, 1),
-                      oz = __shfl_xor_sync(0xffffffffu, sup.z, 1);
-          const int oi = __shfl_xor_sync(0xffffffffu, sidx, 1);
+          const float ox = __shfl_xor_sync(runm, sup.x, 1), oy = __shfl_xor_sync(runm, sup.y, 1),
+                      oz = __shfl_xor_sync(runm, sup.z, 1);
+          const int oi = __shfl_xor_sync(runm, sidx, 1);
           const V3<float> osup = mk<float>(ox, oy, oz);
           g.sup1 = half ? osup : sup;
           g.sup2 = half ? sup : osup;
@@ -506,7 +531,7 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
             pair_of[s] = t;
             st_vol(&ctrl[s], kSlotBusy);
             const uint32_t bar = smem_addr(&bars[s]);
-            const uint32_t dst1 = smem_addr(slots + (size_t)s * sbytes), dst2 = dst1 + bytes1;
+            const uint32_t dst1 = smem_addr(slots + (size_t)s * sbytes), dst2 = dst1 + lay.body2;
             fence_proxy_async();
             mbar_arrive_expect_tx(bar, bytes1 + bytes2);  // release: pair_of is visible to the waiting thread
             tma_bulk_load(dst1, coord1 + (size_t)t * nv1 * 3, bytes1, bar);

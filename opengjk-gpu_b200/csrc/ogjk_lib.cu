@@ -186,11 +186,13 @@ int ws_config(int nv1, int nv2, int* lp) {
   const size_t sb = slot_bytes(nv1, nv2);
   *lp = 1;
   if (ws_fixed_bytes(256) + 256 * sb + kSlotPadBytes <= 227u * 1024u) return 8;
-  if (ws_fixed_bytes(128) + 128 * sb + kSlotPadBytes <= 227u * 1024u) {
-    const char* e = getenv("OGJK_WS_LP");
-    *lp = e ? atoi(e) : 2;
-    return *lp == 2 ? 8 : 4;
+  const char* e = getenv("OGJK_WS_LP");
+  if (e && atoi(e) == 2 &&
+      ws_fixed_bytes(128) + 128 * (size_t)ws_slot_layout(nv1, nv2, 2).stride + kSlotPadBytes <= 227u * 1024u) {
+    *lp = 2;
+    return 8;
   }
+  if (ws_fixed_bytes(128) + 128 * sb + kSlotPadBytes <= 227u * 1024u) return 4;
   return 0;
 }
 int ws_compute_warps(int nv1, int nv2) {
@@ -206,7 +208,7 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float
   if (int rc = device_unified_table(&utab)) return rc;
   if (!t_ticket[dev]) OGJK_CK(cudaMalloc(&t_ticket[dev], sizeof(unsigned)));
   constexpr int nslots = CW * 32 / LP;
-  const size_t smem = (size_t)ws_fixed_bytes(nslots) + kSlotPadBytes + (size_t)nslots * slot_bytes(nv1, nv2);
+  const size_t smem = (size_t)ws_fixed_bytes(nslots) + kSlotPadBytes + (size_t)nslots * ws_slot_layout(nv1, nv2, LP).stride;
   constexpr int threads = (CW + 2) * 32;
   OGJK_CK(cudaFuncSetAttribute(gjk_slots_ws_kernel<CW, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

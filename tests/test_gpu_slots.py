@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def force_kernel():
-    saved = {k: os.environ.get(k) for k in ("OGJK_GJK_KERNEL", "OGJK_WS_MIN_SLOT")}
+    saved = {k: os.environ.get(k) for k in ("OGJK_GJK_KERNEL", "OGJK_WS_MIN_SLOT", "OGJK_WS_LP")}
 
     def setter(name, ws_min_slot=None):
         os.environ["OGJK_GJK_KERNEL"] = name
@@ -50,6 +50,24 @@ def test_slot_kernels_match_oracle(pkg, oracle_mod, force_kernel, kernel, nv1, n
     b = pkg.workloads.random_polytopes(n, nv2, spread, 11, np.float32, stream=2)
     eng, d_a, d_b, d_simp, d_dist, _ = _device_batch(pkg, a, b)
     force_kernel(kernel)
+    eng.gjk_uniform_device(n, nv1, d_a, nv2, d_b, d_simp, d_dist)
+    torch.cuda.synchronize()
+    os_, od = oracle_mod.Oracle("port", np.float32).gjk(a, b, nthreads=8)
+    assert np.array_equal(d_dist.cpu().numpy(), od)
+    assert live_simplex_equal(d_simp.cpu().numpy().view(eng.sdtype), os_)
+    eng.set_stream(0)
+
+
+@pytest.mark.parametrize("nv1,nv2,spread", [(64, 64, 10.0), (64, 48, 3.0), (60, 68, 1.0)])
+def test_ws_two_lanes_per_pair(pkg, oracle_mod, force_kernel, nv1, nv2, spread):
+    """the experimental two-lanes-per-pair mode of the warp-specialised kernel (OGJK_WS_LP=2)"""
+    import torch
+    n = 40000
+    a = pkg.workloads.random_polytopes(n, nv1, spread, 21, np.float32, stream=1)
+    b = pkg.workloads.random_polytopes(n, nv2, spread, 21, np.float32, stream=2)
+    eng, d_a, d_b, d_simp, d_dist, _ = _device_batch(pkg, a, b)
+    force_kernel("slotsws")
+    os.environ["OGJK_WS_LP"] = "2"
     eng.gjk_uniform_device(n, nv1, d_a, nv2, d_b, d_simp, d_dist)
     torch.cuda.synchronize()
     os_, od = oracle_mod.Oracle("port", np.float32).gjk(a, b, nthreads=8)
