@@ -175,11 +175,10 @@ def ours(args, workload):
     d_dist = torch.zeros(n, dtype=torch.float32, device="cuda")
     d_nrm = torch.zeros(n, 3, dtype=torch.float32, device="cuda")
 
-    def gjk():
-        eng.gjk_uniform_device(n, nv, d_a, nv, d_b, d_simp, d_dist)
-
-    def epa():
-        eng.epa_uniform_device(n, nv, d_a, nv, d_b, d_simp, d_dist, d_nrm)
+    def step():
+        # GJK on every pair, then EPA (penetration / witnesses / normal for the colliding pairs, witness normal for
+        # the rest): one library call = the device part of the reference's computeGJKAndEPA
+        eng.gjk_epa_uniform_device(n, nv, d_a, nv, d_b, d_simp, d_dist, d_nrm)
 
     def barrier():
         if world > 1:
@@ -187,27 +186,27 @@ def ours(args, workload):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        gjk()
-        epa()
+        step()
     barrier()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     eng.launch_count(reset=True)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    eng.set_timing(True)  # the library brackets its GJK and EPA launches with CUDA events on this stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    for k in range(args.steps):
-        ev[k][0].record(stream)
-        gjk()
-        ev[k][1].record(stream)
-        epa()
-        ev[k][2].record(stream)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
     barrier()
     launches = eng.launch_count()
-    total_ms = ev[0][0].elapsed_time(ev[-1][2])
-    gjk_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    epa_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    total_ms = e0.elapsed_time(e1)
+    gjk_sum, epa_sum, calls = eng.stage_times()
+    eng.set_timing(False)
+    assert calls == args.steps, (calls, args.steps)
+    gjk_ms, epa_ms = gjk_sum / calls, epa_sum / calls
 
     # ---- end to end through the host-pointer API (computeGJKAndEPA semantics), H2D + D2H inside the timed region
     bd1, _k1 = pkg.make_polytopes(torch.from_numpy(a).pin_memory().numpy())
@@ -215,6 +214,18 @@ def ours(args, workload):
     h_simp = torch.zeros(n * eng.sdtype.itemsize, dtype=torch.uint8).pin_memory().numpy().view(eng.sdtype)
     h_dist = torch.zeros(n, dtype=torch.float32).pin_memory().numpy()
     h_nrm = torch.zeros(n, 3, dtype=torch.float32).pin_memory().numpy()
+    # host->device bandwidth of this box (pinned, 256 MiB), to put the PCIe-bound end-to-end figure in context
+    probe = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    d_probe = torch.empty_like(probe, device="cuda")
+    d_probe.copy_(probe, non_blocking=True)
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    d_probe.copy_(probe, non_blocking=True)
+    p1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = probe.numel() / (p0.elapsed_time(p1) * 1e-3) / 1e9
+    del probe, d_probe
     e2e_steps = max(1, min(args.steps, 5))
     eng.compute_gjk_epa(bd1, bd2, h_simp, h_dist, h_nrm)  # warm-up
     barrier()
@@ -238,8 +249,16 @@ def ours(args, workload):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = bpp * n / (gjk_ms * 1e-3) / 1e9
+        traffic = None  # DRAM bytes per GJK launch from the committed ncu capture of this workload, if any
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = f"{args.workload}:{n}"
+            if key in t:
+                traffic = t[key]["dram_bytes_per_launch"]
+        except Exception:  # noqa: BLE001
+            pass
         value = world * n * args.steps / (total_ms * 1e-3)
-        h2d = 2 * n * nv * 3 * 4 + 2 * n * eng.pdtype.itemsize
+        h2d = 2 * n * nv * 3 * 4  # dense uniform batch: coordinates only, descriptors are read on the host
         d2h = n * (sbytes + 4 + 12)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -248,13 +267,15 @@ def ours(args, workload):
             "config": {"workload": desc, "pairs_per_gpu": n, "verts": nv, "stage": "gjk+epa",
                        "sharding": f"pairs x{world}, no collective", "l2": "inputs (1.5 GB/step) larger than L2"},
             "roofline": {"bound": "hbm", "kernel": "gjk", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                         "algorithmic_bytes_per_pair": bpp, "kernel_ms": gjk_ms},
+                         "algorithmic_bytes_per_pair": bpp, "kernel_ms": gjk_ms,
+                         "timing": "CUDA events recorded by the library around the GJK launch, mean over the timed steps"},
             "kernels_ms": {"gjk": gjk_ms, "epa": epa_ms},
             "gjk_only_pairs_per_sec": n / (gjk_ms * 1e-3),
             "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "ogjk_f32_compute_gjk_epa (host pointers)"},
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "ogjk_f32_compute_gjk_epa (host pointers)",
+                    "h2d_gbs_measured": h2d_gbs},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

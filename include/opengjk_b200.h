@@ -46,6 +46,11 @@ int ogjk_set_stream(void* stream);
 int ogjk_set_sync(int enabled);
 /* Number of kernels this library has launched on the calling thread since the last reset (bench accounting). */
 long long ogjk_launch_count(int reset);
+/* Per-stage device timing of the fused *_gjk_epa_uniform_device calls of this thread: while enabled every call
+ * records CUDA events on the launching stream before GJK, between the stages and after EPA; ogjk_stage_times waits
+ * for them, returns the summed GJK / EPA milliseconds and the number of calls, and resets the list. */
+int ogjk_set_timing(int enabled);
+int ogjk_stage_times(double* gjk_ms, double* epa_ms, int* calls);
 
 #define OGJK_DECLARE_API(P, OGJK_REAL)                                                                          \
   /* ---- high level: host pointers, device memory handled internally -------------------------------- */     \

@@ -133,6 +133,18 @@ class Engine:
     def set_sync(self, enabled: bool):
         self.lib.ogjk_set_sync(ctypes.c_int(int(enabled)))
 
+    def set_timing(self, enabled: bool):
+        """per-stage CUDA-event timing of gjk_epa_uniform_device calls (see ogjk_stage_times)"""
+        self.lib.ogjk_set_timing(ctypes.c_int(int(enabled)))
+
+    def stage_times(self):
+        """-> (gjk_ms, epa_ms, calls) summed over the timed calls since the last query"""
+        g, e, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
+        rc = self.lib.ogjk_stage_times(ctypes.byref(g), ctypes.byref(e), ctypes.byref(c))
+        if rc != 0:
+            raise OgjkError(f"ogjk_stage_times failed ({rc}): {self.lib.ogjk_last_error().decode()}")
+        return g.value, e.value, c.value
+
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.ogjk_launch_count(ctypes.c_int(int(reset))))
 

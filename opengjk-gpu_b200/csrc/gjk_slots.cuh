@@ -173,6 +173,83 @@ OGJK_D void support_slot(const float* body, int nv, const V3<float>& d, unsigned
   }
 }
 
+// Both bodies of a pair in one loop (equal vertex counts): two independent scan streams interleaved, so that the
+// single warp a scheduler has (64+64-vertex slots) finds an independent instruction more often.
+OGJK_D void recover_support(const float* body, const ulonglong2* chunk, int bg, float best, const DirPack& D,
+                            const V3<float>& d, V3<float>& sup, int& sup_idx) {
+  if (best > dot(sup, d)) {
+    float dd[4];
+    dots4(load_block(chunk, bg), D, dd);
+    int k = 3;
+    if (dd[2] == best) k = 2;
+    if (dd[1] == best) k = 1;
+    if (dd[0] == best) k = 0;
+    const int idx = 4 * bg + k;
+    sup = mk<float>(body[3 * idx], body[3 * idx + 1], body[3 * idx + 2]);
+    sup_idx = idx;
+  }
+}
+OGJK_D void support_slots_both(const float* b1, const float* b2, int nv, const V3<float>& v, unsigned zero,
+                               V3<float>& sup1, int& idx1, V3<float>& sup2, int& idx2) {
+  const ulonglong2* c1 = reinterpret_cast<const ulonglong2*>(b1);
+  const ulonglong2* c2 = reinterpret_cast<const ulonglong2*>(b2);
+  const V3<float> nvv = vneg(v);
+  const DirPack D1 = make_dir(nvv, zero), D2 = make_dir(v, zero);
+  float best1 = -INFINITY, best2 = -INFINITY;
+  int bg1 = 0, bg2 = 0;
+  const int groups = nv >> 2;
+  const int pairs = groups >> 1;
+  Block4 a0 = load_block(c1, 0), a1 = load_block(c1, 1);
+  Block4 e0 = load_block(c2, 0), e1 = load_block(c2, 1);
+#pragma unroll 1
+  for (int t = 0; t < pairs; ++t) {
+    const Block4 na0 = load_block(c1, 2 * t + 2), na1 = load_block(c1, 2 * t + 3);
+    const Block4 ne0 = load_block(c2, 2 * t + 2), ne1 = load_block(c2, 2 * t + 3);
+    float da[4], db[4], dc[4], de[4];
+    dots4(a0, D1, da);
+    dots4(e0, D2, dc);
+    dots4(a1, D1, db);
+    dots4(e1, D2, de);
+    const float ma = max4(da), mc = max4(dc), mb = max4(db), me = max4(de);
+    if (ma > best1) {
+      best1 = ma;
+      bg1 = 2 * t;
+    }
+    if (mc > best2) {
+      best2 = mc;
+      bg2 = 2 * t;
+    }
+    if (mb > best1) {
+      best1 = mb;
+      bg1 = 2 * t + 1;
+    }
+    if (me > best2) {
+      best2 = me;
+      bg2 = 2 * t + 1;
+    }
+    a0 = na0;
+    a1 = na1;
+    e0 = ne0;
+    e1 = ne1;
+  }
+  if (groups & 1) {
+    float da[4], dc[4];
+    dots4(a0, D1, da);
+    dots4(e0, D2, dc);
+    const float ma = max4(da), mc = max4(dc);
+    if (ma > best1) {
+      best1 = ma;
+      bg1 = groups - 1;
+    }
+    if (mc > best2) {
+      best2 = mc;
+      bg2 = groups - 1;
+    }
+  }
+  recover_support(b1, c1, bg1, best1, D1, nvv, sup1, idx1);
+  recover_support(b2, c2, bg2, best2, D2, v, sup2, idx2);
+}
+
 struct SlotFetch {
   const float* b1;
   const float* b2;
@@ -195,6 +272,9 @@ __host__ __device__ inline uint32_t slot_bytes(int nv1, int nv2) {
   return units * 16u;
 }
 
+// EQ: both bodies have the same vertex count (selects the interleaved two-body scan; the other scan is not even
+// instantiated then, which keeps the loop body small for the instruction cache)
+template <bool EQ>
 __global__ void __launch_bounds__(kSlotThreads)
 gjk_slots_kernel(const float* __restrict__ coord1, const float* __restrict__ coord2, int nv1, int nv2,
                  SimplexT<float>* __restrict__ simplices, float* __restrict__ distances, unsigned n,
@@ -273,8 +353,12 @@ gjk_slots_kernel(const float* __restrict__ coord1, const float* __restrict__ coo
     }
     if (state == kRunning) {
       ++g.k;
-      support_slot(s1, nv1, vneg(g.v), zero, g.sup1, g.idx1);
-      support_slot(s2, nv2, g.v, zero, g.sup2, g.idx2);
+      if (EQ) {
+        support_slots_both(s1, s2, nv1, g.v, zero, g.sup1, g.idx1, g.sup2, g.idx2);
+      } else {
+        support_slot(s1, nv1, vneg(g.v), zero, g.sup1, g.idx1);
+        support_slot(s2, nv2, g.v, zero, g.sup2, g.idx2);
+      }
       if (gjk_advance_u(g, utab)) {
         SlotFetch fetch{s1, s2};
         V3<float> w1, w2;
@@ -353,7 +437,7 @@ struct RecordFetch {  // vertex "index" = original simplex slot in bits 30..31 (
 // the two lanes of a pair each scan ONE body and exchange the support points with a shuffle, everything else is
 // evaluated redundantly on both -- twice the warps for the same shared memory, so each scheduler has a second warp to
 // issue from while the first waits on a dependency.
-template <int CW, int LP>
+template <int CW, int LP, bool EQ>
 __global__ void __launch_bounds__((CW + 2) * 32)
 gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ coord2, int nv1, int nv2,
                     SimplexT<float>* __restrict__ simplices, float* __restrict__ distances, unsigned n,
@@ -431,8 +515,12 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
       if (state == kRun) {
         ++g.k;
         if (LP == 1) {
-          support_slot(s1, nv1, vneg(g.v), zero, g.sup1, g.idx1);
-          support_slot(s2, nv2, g.v, zero, g.sup2, g.idx2);
+          if (EQ) {
+            support_slots_both(s1, s2, nv1, g.v, zero, g.sup1, g.idx1, g.sup2, g.idx2);
+          } else {
+            support_slot(s1, nv1, vneg(g.v), zero, g.sup1, g.idx1);
+            support_slot(s2, nv2, g.v, zero, g.sup2, g.idx2);
+          }
         } else {
           // this lane's body: half 0 scans body 1 along -v, half 1 scans body 2 along +v
           const float* body = half ? s2 : s1;
@@ -462,6 +550,21 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
         const unsigned idx = base + __popc(fin & ((1u << (lane & ~(LP - 1))) - 1u));
         if (finished) {
           float* rec = ring + (size_t)(idx % kRingRecords) * kRecWords;
+          const SV<float>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
+          // all slot reads first, then all record writes: both are shared memory, so the compiler keeps their order
+          // and a load placed after a store would wait out its full latency before the next store can issue
+          float vert[4][6];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (LP == 1 || (k >> 1) == half) {
+              const SV<float>& q = *sv[k];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                vert[k][c] = s1[3 * q.i1 + c];
+                vert[k][3 + c] = s2[3 * q.i2 + c];
+              }
+            }
+          }
           if (half == 0) {
             rec[0] = __uint_as_float(pair);
             rec[1] = __int_as_float(g.S.n);
@@ -469,22 +572,17 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
             rec[3] = g.v.y;
             rec[4] = g.v.z;
           }
-          const SV<float>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (LP == 1 || (k >> 1) == half) {  // LP = 2: the two lanes write two simplex slots each
+            if (LP == 1 || (k >> 1) == half) {
               const SV<float>& q = *sv[k];
               rec[5 + 5 * k + 0] = q.p.x;
               rec[5 + 5 * k + 1] = q.p.y;
               rec[5 + 5 * k + 2] = q.p.z;
               rec[5 + 5 * k + 3] = __int_as_float(q.i1);
               rec[5 + 5 * k + 4] = __int_as_float(q.i2);
-              rec[25 + 6 * k + 0] = s1[3 * q.i1 + 0];
-              rec[25 + 6 * k + 1] = s1[3 * q.i1 + 1];
-              rec[25 + 6 * k + 2] = s1[3 * q.i1 + 2];
-              rec[25 + 6 * k + 3] = s2[3 * q.i2 + 0];
-              rec[25 + 6 * k + 4] = s2[3 * q.i2 + 1];
-              rec[25 + 6 * k + 5] = s2[3 * q.i2 + 2];
+#pragma unroll
+              for (int c = 0; c < 6; ++c) rec[25 + 6 * k + c] = vert[k][c];
             }
           }
           __threadfence_block();  // record + this thread's slot reads before the two flags

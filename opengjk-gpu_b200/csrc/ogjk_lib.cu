@@ -31,6 +31,15 @@ thread_local cudaStream_t t_stream = nullptr;
 thread_local bool t_sync = true;
 thread_local long long t_launches = 0;
 
+// optional per-stage device timing of the fused GJK+EPA entry points (ogjk_set_timing / ogjk_stage_times): three
+// events per call on the launching stream -- before GJK, between the stages, after EPA
+struct StageEvents {
+  cudaEvent_t e[3];
+};
+thread_local bool t_timing = false;
+thread_local std::vector<StageEvents> t_stage_pool;  // created lazily, re-used
+thread_local size_t t_stage_used = 0;
+
 int fail(const char* what, cudaError_t e) {
   char buf[512];
   snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
@@ -166,16 +175,18 @@ int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, 
   if (int rc = device_unified_table(&utab)) return rc;
   if (!t_ticket[dev]) OGJK_CK(cudaMalloc(&t_ticket[dev], sizeof(unsigned)));
   const size_t smem = (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2);
-  OGJK_CK(cudaFuncSetAttribute(gjk_slots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the interleaved scan needs ~40 more registers: only where shared memory, not registers, bounds occupancy
+  auto kern = (nv1 == nv2 && nv1 >= 32) ? gjk_slots_kernel<true> : gjk_slots_kernel<false>;
+  OGJK_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_slots_kernel, kSlotThreads, smem));
+  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSlotThreads, smem));
   if (per_sm < 1) return fail_msg("slot kernel does not fit on this device");
   long long grid = (long long)sms * per_sm;
   const long long need = ((long long)n + kSlotThreads - 1) / kSlotThreads;
   if (grid > need) grid = need;
   OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
-  gjk_slots_kernel<<<(unsigned)grid, kSlotThreads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab,
-                                                                     t_ticket[dev], slots_prefetch_ahead(), 0u);
+  kern<<<(unsigned)grid, kSlotThreads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab, t_ticket[dev],
+                                                         slots_prefetch_ahead(), 0u);
   return finish_launch("gjk slots kernel");
 }
 
@@ -210,16 +221,17 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float
   constexpr int nslots = CW * 32 / LP;
   const size_t smem = (size_t)ws_fixed_bytes(nslots) + kSlotPadBytes + (size_t)nslots * ws_slot_layout(nv1, nv2, LP).stride;
   constexpr int threads = (CW + 2) * 32;
-  OGJK_CK(cudaFuncSetAttribute(gjk_slots_ws_kernel<CW, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = (LP == 1 && nv1 == nv2) ? gjk_slots_ws_kernel<CW, LP, true> : gjk_slots_ws_kernel<CW, LP, false>;
+  OGJK_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_slots_ws_kernel<CW, LP>, threads, smem));
+  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) return fail_msg("slot kernel does not fit on this device");
   long long grid = (long long)sms * per_sm;
   const long long need = ((long long)n + nslots - 1) / nslots;
   if (grid > need) grid = need;
   OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
-  gjk_slots_ws_kernel<CW, LP><<<(unsigned)grid, threads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n,
-                                                                           utab, t_ticket[dev], 0u, nrm, queue, count);
+  kern<<<(unsigned)grid, threads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab, t_ticket[dev], 0u,
+                                                    nrm, queue, count);
   return finish_launch("gjk slots (warp-specialised) kernel");
 }
 int launch_gjk_slots_ws(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist,
@@ -232,10 +244,12 @@ int launch_gjk_slots_ws(int n, int nv1, const float* c1, int nv2, const float* c
   return 1;
 }
 
-// policy: the warp-specialised kernel pays off when slots are so large that few compute warps fit an SM
+// policy: the warp-specialised kernel pays off when slots are so large that the self-service kernel would be down
+// to one 4-warp CTA per SM (measured on B200: 64+64 vertices 1.28e9 vs 1.15e9 pairs/s; at 32+32 vertices, where
+// the self-service kernel runs 8 warps per SM, it is the other way round: 1.6e9 vs 2.6e9)
 bool use_ws_kernel(int nv1, int nv2) {
   const char* e = getenv("OGJK_WS_MIN_SLOT");  // development override (bytes)
-  const int thr = e ? atoi(e) : 700;
+  const int thr = e ? atoi(e) : 880;
   return ws_compute_warps(nv1, nv2) != 0 && (int)slot_bytes(nv1, nv2) >= thr;
 }
 
@@ -348,10 +362,25 @@ int launch_epa(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distance
 // GJK then EPA on a dense uniform device batch.  When the warp-specialised slot kernel applies, its finisher warp
 // also does the EPA gate (normals of separated pairs, queue of colliding ones), which saves the gate kernel's pass
 // over distances + witnesses; otherwise the two stages run back to back as in the reference (openGJK.cu:2854-2883).
+int stage_mark(int which) {
+  if (!t_timing) return 0;
+  if (which == 0) {
+    if (t_stage_used == t_stage_pool.size()) {
+      StageEvents se;
+      for (auto& ev : se.e) OGJK_CK(cudaEventCreate(&ev));
+      t_stage_pool.push_back(se);
+    }
+    ++t_stage_used;
+  }
+  OGJK_CK(cudaEventRecord(t_stage_pool[t_stage_used - 1].e[which], t_stream));
+  return 0;
+}
+
 template <typename T>
 int launch_gjk_epa_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist, T* nrm) {
   if (!nrm) return fail_msg("contact_normals must not be NULL on the device path");
   UniformSource<T> src{c1, c2, nv1, nv2};
+  if (int rc = stage_mark(0)) return rc;
   if constexpr (sizeof(T) == 4) {
     const bool aligned = (((uintptr_t)c1 | (uintptr_t)c2) & 15u) == 0 && nv1 % 4 == 0 && nv2 % 4 == 0;
     const int force = forced_kernel();
@@ -361,16 +390,23 @@ int launch_gjk_epa_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, Si
       OGJK_CK(cudaMemsetAsync(scratch, 0, 2 * sizeof(int), t_stream));
       const bool sync_saved = t_sync;
       t_sync = false;  // no need to synchronise between the two stages
-      const int rc = launch_gjk_slots_ws(n, nv1, c1, nv2, c2, simp, dist, nrm, scratch + 2, scratch);
+      int rc = launch_gjk_slots_ws(n, nv1, c1, nv2, c2, simp, dist, nrm, scratch + 2, scratch);
       t_sync = sync_saved;
-      if (rc) return rc;
-      return launch_epa_queue<T, UniformSource<T>>(src, n, simp, dist, nrm, scratch + 2, scratch);
+      if (!rc) rc = stage_mark(1);
+      if (!rc) rc = launch_epa_queue<T, UniformSource<T>>(src, n, simp, dist, nrm, scratch + 2, scratch);
+      if (!rc) rc = stage_mark(2);
+      return rc;
     }
   }
+  const bool sync_saved = t_sync;
+  t_sync = false;
   int rc = launch_gjk_uniform<T>(n, nv1, c1, nv2, c2, simp, dist);
   if (rc > 0) rc = launch_gjk_generic<T>(src, n, (nv1 + nv2) / 2, simp, dist);
-  if (rc) return rc;
-  return launch_epa<T>(src, n, simp, dist, nrm);
+  t_sync = sync_saved;
+  if (!rc) rc = stage_mark(1);
+  if (!rc) rc = launch_epa<T>(src, n, simp, dist, nrm);
+  if (!rc) rc = stage_mark(2);
+  return rc;
 }
 
 // numpoints of the first descriptor of a device array (vertex-count hint for lane selection)
@@ -745,6 +781,27 @@ int ogjk_set_stream(void* stream) {
 }
 int ogjk_set_sync(int enabled) {
   t_sync = enabled != 0;
+  return 0;
+}
+int ogjk_set_timing(int enabled) {
+  t_timing = enabled != 0;
+  t_stage_used = 0;
+  return 0;
+}
+int ogjk_stage_times(double* gjk_ms, double* epa_ms, int* calls) {
+  double g = 0, e = 0;
+  for (size_t i = 0; i < t_stage_used; ++i) {
+    float a = 0, b = 0;
+    OGJK_CK(cudaEventSynchronize(t_stage_pool[i].e[2]));
+    OGJK_CK(cudaEventElapsedTime(&a, t_stage_pool[i].e[0], t_stage_pool[i].e[1]));
+    OGJK_CK(cudaEventElapsedTime(&b, t_stage_pool[i].e[1], t_stage_pool[i].e[2]));
+    g += a;
+    e += b;
+  }
+  if (gjk_ms) *gjk_ms = g;
+  if (epa_ms) *epa_ms = e;
+  if (calls) *calls = (int)t_stage_used;
+  t_stage_used = 0;
   return 0;
 }
 long long ogjk_launch_count(int reset) {
