@@ -237,15 +237,31 @@ OGJK_HD bool gjk_advance(GjkState<T>& g, const uint32_t* __restrict__ t2, const 
 // operands), and the surviving points are picked out of {slot0, slot1, slot2, a} by the leaf's permutation.
 // In a thread-per-pair warp this replaces three serialised divergent paths by a single one.
 // `tab` = the 16-bit unified table (any address space).
+// The two exit tests that precede the sub-algorithm (openGJK.cu:1363-1378): true = the pair has terminated with the
+// simplex it already holds.  Split out so that the slot kernel can hand a finished pair's slot back for refilling
+// before it runs the sub-algorithm of the others.
 template <typename T>
-OGJK_HD bool gjk_advance_u(GjkState<T>& g, const uint16_t* __restrict__ tab) {
+OGJK_HD bool gjk_converged_u(const GjkState<T>& g) {
   const T eps_rel = Tol<T>::eps_rel();
   const T eps_tot = Tol<T>::eps_tot();
   const V3<T> a = vsub(g.sup1, g.sup2);
   const T vv = norm2(g.v);
   const T gap = sub_rn(vv, dot(g.v, a));
   if (gap <= mul_rn(eps_rel, vv) || gap < eps_tot) return true;
-  if (vv < mul_rn(eps_rel, eps_rel)) return true;
+  return vv < mul_rn(eps_rel, eps_rel);
+}
+template <typename T>
+OGJK_HD bool gjk_substep_u(GjkState<T>& g, const uint16_t* __restrict__ tab);
+template <typename T>
+OGJK_HD bool gjk_advance_u(GjkState<T>& g, const uint16_t* __restrict__ tab) {
+  if (gjk_converged_u(g)) return true;
+  return gjk_substep_u(g, tab);
+}
+// everything after the two pre-tests: add the new point, sub-algorithm, running max, third exit test
+template <typename T>
+OGJK_HD bool gjk_substep_u(GjkState<T>& g, const uint16_t* __restrict__ tab) {
+  const T eps_tot = Tol<T>::eps_tot();
+  const V3<T> a = vsub(g.sup1, g.sup2);
 
   const int m = g.S.n;  // 1..3 older points
   const V3<T> pp = mk<T>(mul_rn(a.x, a.x), mul_rn(a.y, a.y), mul_rn(a.z, a.z));

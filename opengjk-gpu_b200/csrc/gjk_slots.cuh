@@ -540,15 +540,19 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
         }
         finished = gjk_advance_u(g, utab);
       }
-      const unsigned fin = __ballot_sync(0xffffffffu, finished && half == 0);
-      if (fin) {
+      // (Retiring the pairs that end at the pre-tests before the others run the sub-algorithm, and pulling upcoming
+      // pairs into L2 with cp.async.bulk.prefetch from the loader, were both measured and both lost: 1.30e9 and
+      // 0.98-1.15e9 pairs/s against 1.36e9 -- profiles/r1_gjk_kernels_ab.txt.)
+      auto retire = [&](bool done) {
+        const unsigned fin = __ballot_sync(0xffffffffu, done && half == 0);
+        if (!fin) return;
         const unsigned cnt = __popc(fin);
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(&ring_ctl[0], cnt);
         base = __shfl_sync(0xffffffffu, base, 0);
         while ((int)(base + cnt - ld_vol(&ring_ctl[1])) > kRingRecords) __nanosleep(64);  // ring full: wait for space
         const unsigned idx = base + __popc(fin & ((1u << (lane & ~(LP - 1))) - 1u));
-        if (finished) {
+        if (done) {
           float* rec = ring + (size_t)(idx % kRingRecords) * kRecWords;
           const SV<float>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
           // all slot reads first, then all record writes: both are shared memory, so the compiler keeps their order
@@ -588,14 +592,15 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
           __threadfence_block();  // record + this thread's slot reads before the two flags
         }
         __syncwarp();
-        if (finished) {
+        if (done) {
           if (half == 0) {
             st_vol(&ready[idx % kRingRecords], idx / kRingRecords + 1u);
             st_vol(&ctrl[cslot], kSlotFree);
           }
           state = kWait;
         }
-      }
+      };
+      retire(finished);
     }
     __syncwarp();
     if (lane == 0) {
