@@ -1,0 +1,549 @@
+// epa_group.cuh -- Expanding Polytope Algorithm with a sub-warp GROUP of G lanes per colliding pair.
+//
+// Same algorithm, same arithmetic and the same tie-breaks as epa_pair (epa_kernel.cuh; contract: SURVEY.md Appendix
+// A.6 = the reference's scalar EPA, GJK/cpu/EPA.c:362-863), but a different machine mapping.  profiles/
+// r1c_epa_queue_cfg3.txt shows the warp-per-pair kernel issue-bound (77 % of the issue slots) with a flat profile:
+// an expansion works on ~20 live faces, a handful of dying faces, <= 18 horizon edges and 4-6 new faces, so most of
+// its ~560 warp instructions per iteration run with a fraction of the 32 lanes doing anything.  Here 8 lanes share a
+// pair and a warp carries FOUR pairs through one instruction stream:
+//   * the kernel is a persistent state machine -- a group that finishes its pair pulls the next one from the queue
+//     while the other groups of the warp keep expanding -- so the four groups stay in one loop;
+//   * the expansion step is executed by all 32 lanes in lock step: collectives name the whole warp (each group looks
+//     at its own 8 bits / shuffles within its 8-lane segment), loops run to the maximum trip count over the four
+//     groups with per-group predicates.  (Collectives that name only the group's lanes are legal but ptxas
+//     serialises them over the distinct masks -- the first version of this kernel ran at 16 active lanes and was
+//     slower than warp-per-pair.)  Set-up and reporting, once per pair, stay group-masked and divergent;
+//   * reductions are 3-level xor butterflies on (value, lowest index);
+//   * face slot f belongs to lane f % G of the group; per-face passes run over the live slot range only;
+//   * both bodies' vertices are cached in registers (<= 64 per body: 8 per lane).
+// One warp per CTA (19 KB of shared memory for its four work areas), 11 CTAs per SM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "epa_kernel.cuh"
+
+namespace ogjk {
+
+template <int G>
+struct Grp {
+  static_assert(G == 8 || G == 16 || G == 32, "group size");
+  int lane;       // lane within the group
+  unsigned mask;  // warp lane mask of the group
+  int shift;      // first warp lane of the group
+  // whole_warp = false: collectives name only this group's lanes (legal anywhere the group is convergent, but ptxas
+  // serialises votes over the distinct masks).  whole_warp = true: collectives name all 32 lanes -- only for code that
+  // the four groups of a warp execute together; every group still sees just its own lanes' bits / values.
+  OGJK_D explicit Grp(int wlane, bool whole_warp = false) {
+    lane = wlane & (G - 1);
+    shift = wlane & ~(G - 1);
+    mask = (G == 32 || whole_warp) ? 0xffffffffu : (((1u << G) - 1u) << shift);
+  }
+  OGJK_D unsigned ballot(bool p) const {  // bit i = group lane i
+    return (__ballot_sync(mask, p) >> shift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+  }
+  OGJK_D bool any(bool p) const { return ballot(p) != 0u; }
+  OGJK_D void sync() const { __syncwarp(mask); }
+  OGJK_D unsigned below() const { return (1u << lane) - 1u; }
+  OGJK_D int bcast(int v, int src) const { return __shfl_sync(mask, v, src, G); }
+};
+
+// (max value, lowest index) over the group: xor butterfly; every lane ends with the same pair
+template <typename T, int G>
+OGJK_D void grp_argmax(const Grp<G>& g, T& best, int& bi) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const T ov = __shfl_xor_sync(g.mask, best, o, G);
+    const int oi = __shfl_xor_sync(g.mask, bi, o, G);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+}
+template <typename T, int G>
+OGJK_D void grp_argmin(const Grp<G>& g, T& best, int& bi) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const T ov = __shfl_xor_sync(g.mask, best, o, G);
+    const int oi = __shfl_xor_sync(g.mask, bi, o, G);
+    if (ov < best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+}
+
+// this lane's share of a body: vertices lane, lane + G, ... (cached in registers when the body has <= 64 vertices)
+template <typename T, int G>
+struct GrpVerts {
+  static constexpr int kPerLane = 64 / G;
+  V3<T> p[kPerLane];
+  bool cached;
+};
+template <typename T, int G>
+OGJK_D void cache_grp_verts(const BodyRef<T>& A, int glane, GrpVerts<T, G>& r) {
+  r.cached = A.n <= 64;
+#pragma unroll
+  for (int k = 0; k < GrpVerts<T, G>::kPerLane; ++k) {
+    const int i = glane + G * k;
+    r.p[k] = (r.cached && i < A.n) ? load3(A.c, i) : mk<T>(T(0), T(0), T(0));
+  }
+}
+template <typename T, int G>
+OGJK_D void grp_lane_support(const BodyRef<T>& A, const GrpVerts<T, G>& L, const V3<T>& d, bool negate, int glane,
+                             T& best, int& bi) {
+  best = (T)-1e10f;
+  bi = 0x7fffffff;
+  if (L.cached) {
+#pragma unroll
+    for (int k = 0; k < GrpVerts<T, G>::kPerLane; ++k) {
+      const int i = glane + G * k;
+      T sv = dot(L.p[k].x, L.p[k].y, L.p[k].z, d);
+      if (negate) sv = -sv;
+      if (i < A.n && sv > best) {
+        best = sv;
+        bi = i;
+      }
+    }
+  } else {
+    for (int i = glane; i < A.n; i += G) {  // per-lane trip counts: no collective inside
+      const V3<T> p = load3(A.c, i);
+      T sv = dot(p.x, p.y, p.z, d);
+      if (negate) sv = -sv;
+      if (sv > best) {
+        best = sv;
+        bi = i;
+      }
+    }
+  }
+}
+// EPA.c:307-344 (see epa_support)
+template <typename T, int G>
+OGJK_D bool grp_support(const Grp<G>& g, const BodyRef<T>& A, const BodyRef<T>& B, const GrpVerts<T, G>& LA,
+                        const GrpVerts<T, G>& LB, const V3<T>& d, V3<T>& w, int& i1, int& i2) {
+  T b1, b2;
+  int k1, k2;
+  grp_lane_support<T, G>(A, LA, d, false, g.lane, b1, k1);
+  grp_lane_support<T, G>(B, LB, d, true, g.lane, b2, k2);
+  grp_argmax<T, G>(g, b1, k1);
+  grp_argmax<T, G>(g, b2, k2);
+  if (k1 == 0x7fffffff || k2 == 0x7fffffff) return false;
+  w = vsub(load3(A.c, k1), load3(B.c, k2));
+  i1 = k1;
+  i2 = k2;
+  return true;
+}
+
+// closest live face among slots [0, G*nj): smallest distance >= 0, lowest slot on ties (EPA.c:606-617); -1 if none
+// `trips` >= nj is the loop bound (equal to nj, or the maximum over the warp's groups when they run in lock step)
+template <typename T, int G>
+OGJK_D int grp_closest_face(const Grp<G>& g, const EpaWork<T>& W, int nj, int trips, T& dist) {
+  T best = (T)1e10f;
+  int bf = 0x7fffffff;
+  for (int j = 0; j < trips; ++j) {
+    if (j < nj) {
+      const int f = g.lane + G * j;
+      const bool live = (W.fv[f] >> 24) != 0;
+      const T d = W.fd[f];
+      if (live && d >= T(0) && d < best) {
+        best = d;
+        bf = f;
+      }
+    }
+  }
+  grp_argmin<T, G>(g, best, bf);
+  dist = best;
+  return bf == 0x7fffffff ? -1 : bf;
+}
+
+template <typename T>
+struct EpaGroupConfig {
+  static constexpr int kGroup = 8;
+  static constexpr int kThreads = 32;  // one warp per CTA: kThreads / kGroup work areas
+};
+
+template <typename T, int G, typename Source>
+__global__ void __launch_bounds__(EpaGroupConfig<T>::kThreads)
+epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
+                 T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char epa_smem[];
+  EpaWork<T>* work = reinterpret_cast<EpaWork<T>*>(epa_smem);
+  const int wlane = threadIdx.x & 31;
+  const Grp<G> g(wlane);
+  EpaWork<T>& W = work[threadIdx.x / G];
+  const int count = counters[0];
+  const T eps = Tol<T>::eps();
+  const T tol = Tol<T>::eps_tot();
+
+  enum { kIdle = 0, kExpand = 1, kReport = 2, kExit = 3 };
+  int phase = kIdle;
+  // per-pair state, replicated on the lanes of the group
+  long long pair = 0;
+  SimplexT<T>* sp = nullptr;
+  T* nrm_out = nullptr;
+  BodyRef<T> A, B;
+  A.c = B.c = nullptr;
+  A.n = B.n = 0;
+  GrpVerts<T, G> LA, LB;
+  LA.cached = LB.cached = false;
+  int nv_in = 0, nv = 0, iter = 0, hi = 4;
+  V3<T> centroid = mk<T>(T(0), T(0), T(0));
+  bool reported = false;
+  int report_face = -1;
+  T report_d = T(0);
+
+  for (;;) {
+    // ================================ fetch + set up the next pair =================================================
+    if (phase == kIdle) {
+      int q = 0;
+      if (g.lane == 0) q = atomicAdd(&counters[1], 1);
+      q = g.bcast(q, 0);
+      if (q >= count) {
+        phase = kExit;
+      } else {
+        pair = queue[q];
+        sp = simplices + pair;
+        nrm_out = normals + 3 * (size_t)pair;
+        src.get(pair, A, B);
+        cache_grp_verts<T, G>(A, g.lane, LA);
+        cache_grp_verts<T, G>(B, g.lane, LB);
+        g.sync();  // the previous pair's last reads of the work area are done
+        nv_in = sp->nvrtx;
+        nv = nv_in;
+        if (g.lane < 4) {
+          W.vx[g.lane] = sp->vrtx[g.lane][0];
+          W.vy[g.lane] = sp->vrtx[g.lane][1];
+          W.vz[g.lane] = sp->vrtx[g.lane][2];
+          W.src1[g.lane] = sp->vrtx_idx[g.lane][0];
+          W.src2[g.lane] = sp->vrtx_idx[g.lane][1];
+        }
+        g.sync();
+
+        // "no progress" exit shared by the regrow steps (EPA.c:409-418, 474-483, 559-567, 571-582)
+        auto touch_exit = [&](int i1, int i2) {
+          if (g.lane == 0) {
+            const V3<T> w1 = load3(A.c, i1), w2 = load3(B.c, i2);
+            const V3<T> nr = normal_from_witnesses(w1, w2);
+            distances[pair] = T(0);
+            sp->witnesses[0][0] = w1.x; sp->witnesses[0][1] = w1.y; sp->witnesses[0][2] = w1.z;
+            sp->witnesses[1][0] = w2.x; sp->witnesses[1][1] = w2.y; sp->witnesses[1][2] = w2.z;
+            nrm_out[0] = nr.x; nrm_out[1] = nr.y; nrm_out[2] = nr.z;
+            sp->nvrtx = nv;
+            for (int j = nv_in < 0 ? 0 : nv_in; j < nv && j < 4; ++j) {
+              sp->vrtx[j][0] = W.vx[j]; sp->vrtx[j][1] = W.vy[j]; sp->vrtx[j][2] = W.vz[j];
+              sp->vrtx_idx[j][0] = W.src1[j]; sp->vrtx_idx[j][1] = W.src2[j];
+            }
+          }
+        };
+        // candidate accepted iff at squared distance >= eps^2 from every current vertex (EPA.c:389-397 etc.)
+        auto is_new = [&](const V3<T>& p) {
+          const T eps_sq = mul_rn(eps, eps);
+          bool fresh = true;
+          for (int q2 = 0; q2 < nv; ++q2) {
+            const T dx = sub_rn(p.x, W.vx[q2]), dy = sub_rn(p.y, W.vy[q2]), dz = sub_rn(p.z, W.vz[q2]);
+            if (add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz)) < eps_sq) fresh = false;
+          }
+          return fresh;
+        };
+        auto push = [&](const V3<T>& p, int i1, int i2) {
+          g.sync();
+          if (g.lane == 0) {
+            W.vx[nv] = p.x; W.vy[nv] = p.y; W.vz[nv] = p.z;
+            W.src1[nv] = i1; W.src2[nv] = i2;
+          }
+          ++nv;
+          g.sync();
+        };
+
+        // ---- regrow a degenerate simplex to a tetrahedron (EPA.c:375-583) -----------------------------------------
+        bool ok_setup = true;
+        if (nv != 4) {
+          V3<T> p;
+          int i1 = 0, i2 = 0;
+          if (ok_setup && nv == 1) {
+            const bool ok = grp_support<T, G>(g, A, B, LA, LB, work_vertex(W, 0), p, i1, i2);
+            if (ok && is_new(p)) push(p, i1, i2);
+            else { touch_exit(i1, i2); ok_setup = false; }
+          }
+          if (ok_setup && nv == 2) {
+            const V3<T> edge = vsub(work_vertex(W, 1), work_vertex(W, 0));
+            V3<T> axis = mk<T>(T(1), T(0), T(0));
+            const T len = sqrt_rn(norm2(edge));
+            if (len > eps && fabs_(edge.x) > mul_rn((T)0.9f, len)) axis = mk<T>(T(0), T(1), T(0));
+            V3<T> dir = cross(edge, axis);
+            if (norm2(dir) < eps) dir = cross(edge, mk<T>(T(0), T(0), T(1)));
+            const bool ok = grp_support<T, G>(g, A, B, LA, LB, dir, p, i1, i2);
+            if (ok && is_new(p)) push(p, i1, i2);
+            else { touch_exit(i1, i2); ok_setup = false; }
+          }
+          if (ok_setup && nv == 3) {
+            const V3<T> v0 = work_vertex(W, 0);
+            V3<T> dir = cross(vsub(work_vertex(W, 1), v0), vsub(work_vertex(W, 2), v0));
+            bool ok = grp_support<T, G>(g, A, B, LA, LB, dir, p, i1, i2);
+            if (ok && is_new(p)) {
+              push(p, i1, i2);
+            } else {
+              dir = vneg(dir);
+              ok = grp_support<T, G>(g, A, B, LA, LB, dir, p, i1, i2);
+              if (ok && is_new(p)) push(p, i1, i2);
+              else { touch_exit(i1, i2); ok_setup = false; }
+            }
+          }
+          if (ok_setup && nv != 4) {  // nvrtx outside 1..4 on input (EPA.c:571-582)
+            const int best = nv > 0 ? (nv - 1 < 3 ? nv - 1 : 3) : 0;
+            touch_exit(sp->vrtx_idx[best][0], sp->vrtx_idx[best][1]);
+            ok_setup = false;
+          }
+        }
+        if (ok_setup) {
+          // ---- tetrahedron (EPA.c:144-235) ---------------------------------------------------------------------------
+          centroid = mk<T>(T(0), T(0), T(0));
+#pragma unroll
+          for (int q2 = 0; q2 < 4; ++q2) {
+            centroid.x = add_rn(centroid.x, mul_rn(W.vx[q2], (T)0.25f));
+            centroid.y = add_rn(centroid.y, mul_rn(W.vy[q2], (T)0.25f));
+            centroid.z = add_rn(centroid.z, mul_rn(W.vz[q2], (T)0.25f));
+          }
+          for (int f = g.lane; f < kEpaMaxFaces; f += G) W.fv[f] = 0u;
+          g.sync();
+          if (g.lane < 4) {
+            // faces (0,1,2) (0,3,1) (0,2,3) (1,3,2)
+            const int l = g.lane;
+            const int a = l == 3 ? 1 : 0;
+            const int b = l == 0 ? 1 : (l == 2 ? 2 : 3);
+            const int c = l == 0 ? 2 : (l == 1 ? 1 : (l == 2 ? 3 : 2));
+            bool degenerate = false;
+            const uint32_t word = make_face(W, l, a, b, c, centroid, degenerate);
+            W.fv[l] = degenerate ? (word & 0x00ffffffu) : word;
+          }
+          g.sync();
+          iter = 0;
+          hi = 4;
+          reported = false;
+          report_face = -1;
+          report_d = T(0);
+          phase = kExpand;
+        }
+      }
+    }
+    if (__all_sync(0xffffffffu, phase == kExit)) break;
+
+    // ================================ one expansion step (EPA.c:596-826) ==========================================
+    // Executed by ALL lanes of the warp in lock step (collectives name the whole warp, loops run to the maximum trip
+    // count over the four groups); `act` = this lane's group is expanding.  A group that stops mid-way clears `act`
+    // and idles to the end of the block.
+    if (__any_sync(0xffffffffu, phase == kExpand)) {
+      const Grp<G> gw(wlane, true);
+      bool act = phase == kExpand;
+      if (__any_sync(0xffffffffu, act && iter >= kEpaMaxIters)) {  // iteration cap (EPA.c:828-863): rare
+        const bool cap = act && iter >= kEpaMaxIters;
+        T cd;
+        const int cf = grp_closest_face<T, G>(gw, W, cap ? kEpaMaxFaces / G : 0, kEpaMaxFaces / G, cd);
+        if (cap) {
+          if (cf >= 0) {
+            reported = true;
+            report_face = cf;
+            report_d = cd;
+          }
+          phase = kReport;
+          act = false;
+        }
+      }
+      if (act) ++iter;
+      const int nj = act ? (hi + G - 1) / G : 0;
+      const int njw = __reduce_max_sync(0xffffffffu, nj);
+      T cd;
+      int cf = grp_closest_face<T, G>(gw, W, nj, njw, cd);
+      if (act && cf < 0) {
+        phase = kReport;
+        act = false;
+      }
+      if (!act) cf = 0;
+      const V3<T> cn = mk<T>(W.nx[cf], W.ny[cf], W.nz[cf]);
+      V3<T> w = mk<T>(T(0), T(0), T(0));
+      int i1 = 0, i2 = 0;
+      {
+        T b1 = (T)-1e10f, b2 = (T)-1e10f;
+        int k1 = 0x7fffffff, k2 = 0x7fffffff;
+        if (act) {  // no collective inside; idle groups may hold stale body descriptors
+          grp_lane_support<T, G>(A, LA, cn, false, g.lane, b1, k1);
+          grp_lane_support<T, G>(B, LB, cn, true, g.lane, b2, k2);
+        }
+        grp_argmax<T, G>(gw, b1, k1);
+        grp_argmax<T, G>(gw, b2, k2);
+        if (act && (k1 == 0x7fffffff || k2 == 0x7fffffff)) {
+          phase = kReport;
+          act = false;
+        }
+        if (act) {
+          w = vsub(load3(A.c, k1), load3(B.c, k2));
+          i1 = k1;
+          i2 = k2;
+        }
+      }
+      bool stop = sub_rn(dot(cn, w), cd) < tol;
+      {  // duplicate of an existing polytope vertex? (EPA.c:654-665)
+        const T eps_sq = mul_rn(eps, eps);
+        const int nvw = __reduce_max_sync(0xffffffffu, act ? nv : 0);
+        bool dup = false;
+        for (int q2 = g.lane; q2 < nvw; q2 += G) {
+          if (act && q2 < nv) {
+            const T dx = sub_rn(w.x, W.vx[q2]), dy = sub_rn(w.y, W.vy[q2]), dz = sub_rn(w.z, W.vz[q2]);
+            if (add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz)) < eps_sq) dup = true;
+          }
+        }
+        if (gw.any(dup)) stop = true;
+      }
+      if (act && stop) {
+        reported = true;
+        report_face = cf;
+        report_d = cd;
+        phase = kReport;
+        act = false;
+      }
+
+      // add the vertex, move the running centroid (EPA.c:686-699)
+      const int newv = nv;
+      if (act) {
+        if (g.lane == 0) {
+          W.vx[newv] = w.x; W.vy[newv] = w.y; W.vz[newv] = w.z;
+          W.src1[newv] = i1; W.src2[newv] = i2;
+        }
+        ++nv;
+        const T inv_n = div_rn(T(1), (T)nv);
+        centroid.x = add_rn(centroid.x, mul_rn(sub_rn(w.x, centroid.x), inv_n));
+        centroid.y = add_rn(centroid.y, mul_rn(sub_rn(w.y, centroid.y), inv_n));
+        centroid.z = add_rn(centroid.z, mul_rn(sub_rn(w.z, centroid.z), inv_n));
+      }
+
+      // faces that see the new vertex die; their directed edges go to the scratch list in (slot, corner) order
+      int nvis = 0;
+      for (int j = 0; j < njw; ++j) {
+        const int f = g.lane + G * j;
+        uint32_t word = 0;
+        bool sees = false;
+        if (act && j < nj) {
+          word = W.fv[f];
+          if (word >> 24) {
+            const int a = word & 0xff;
+            const V3<T> diff = vsub(w, work_vertex(W, a));
+            sees = dot(mk<T>(W.nx[f], W.ny[f], W.nz[f]), diff) > eps;
+          }
+        }
+        const unsigned vm = gw.ballot(sees);
+        if (sees) {
+          const int rank = nvis + __popc(vm & g.below());
+          const uint32_t a = word & 0xff, b = (word >> 8) & 0xff, c = (word >> 16) & 0xff;
+          W.edge[3 * rank + 0] = (uint16_t)((a << 8) | b);
+          W.edge[3 * rank + 1] = (uint16_t)((b << 8) | c);
+          W.edge[3 * rank + 2] = (uint16_t)((c << 8) | a);
+          W.fv[f] = word & 0x00ffffffu;  // retire
+        }
+        nvis += __popc(vm);
+      }
+      __syncwarp();
+      const int nedge = 3 * nvis;  // 0 for inactive groups
+      const int nedgew = __reduce_max_sync(0xffffffffu, nedge);
+
+      // r-th lowest free slot for r < nedge: slots at or above `hi` are all free, so [0, hi + nedge) always holds
+      // enough -- unless the 128 slots run out, in which case the remaining edges are dropped (EPA.c:775)
+      int nfree = 0;
+      {
+        const int limit = !act ? 0 : (hi + nedge < kEpaMaxFaces ? hi + nedge : kEpaMaxFaces);
+        const int limitw = __reduce_max_sync(0xffffffffu, limit);
+        for (int j = 0; G * j < limitw; ++j) {
+          const int f = g.lane + G * j;
+          const bool is_free = G * j < limit && (W.fv[f] >> 24) == 0;
+          const unsigned fm = gw.ballot(is_free);
+          if (is_free) W.rank2slot[nfree + __popc(fm & g.below())] = (uint8_t)f;
+          nfree += __popc(fm);
+        }
+      }
+      __syncwarp();
+
+      // horizon = edges that occur exactly once (EPA.c:745-759); each gets the next lowest free slot, in edge
+      // order (EPA.c:761-775)
+      int base_rank = 0;
+      bool any_degenerate = false;
+      for (int e0 = 0; e0 < nedgew; e0 += G) {
+        const int e = e0 + g.lane;
+        bool keep = e < nedge;
+        uint32_t key = 0, rev = 0;
+        if (keep) {
+          key = W.edge[e];
+          rev = ((key & 0xff) << 8) | (key >> 8);
+        }
+        for (int x = 0; x < nedgew; ++x) {
+          if (x < nedge) {
+            const uint32_t other = W.edge[x];
+            if (x != e && (other == key || other == rev)) keep = false;
+          }
+        }
+        const unsigned keepm = gw.ballot(keep);
+        if (keep) {
+          const int q2 = base_rank + __popc(keepm & g.below());
+          if (q2 < nfree) {
+            const int slot = W.rank2slot[q2];
+            bool degenerate = false;
+            const uint32_t word = make_face(W, slot, (int)(key >> 8), (int)(key & 0xff), newv, centroid, degenerate);
+            W.fv[slot] = word;
+            if (degenerate) any_degenerate = true;
+          }
+        }
+        base_rank += __popc(keepm);
+      }
+      if (act) {
+        const int used = base_rank < nfree ? base_rank : nfree;
+        if (used > 0) {
+          const int top = (int)W.rank2slot[used - 1] + 1;  // ranks ascend with slots
+          hi = top > hi ? top : hi;
+        }
+      }
+      __syncwarp();
+      // degenerate new faces stay "live" while slots are being handed out and are retired at the next plane
+      // recomputation in the reference (EPA.c:125-128, 599-604) -- i.e. now.
+      if (__any_sync(0xffffffffu, any_degenerate)) {
+        const bool mine = gw.any(any_degenerate);
+        if (mine)
+          for (int f = g.lane; f < kEpaMaxFaces; f += G)
+            if ((W.fv[f] >> 24) && W.fd[f] == (T)1e10) W.fv[f] &= 0x00ffffffu;
+        __syncwarp();
+      }
+    }
+
+    // ================================ outputs ======================================================================
+    if (phase == kReport) {
+      if (g.lane == 0) {
+        if (nv_in != 4) {  // the regrown simplex is part of the result (EPA.c modifies it in place)
+          sp->nvrtx = 4;
+          for (int j = nv_in < 0 ? 0 : nv_in; j < 4; ++j) {
+            sp->vrtx[j][0] = W.vx[j]; sp->vrtx[j][1] = W.vy[j]; sp->vrtx[j][2] = W.vz[j];
+            sp->vrtx_idx[j][0] = W.src1[j]; sp->vrtx_idx[j][1] = W.src2[j];
+          }
+        }
+        if (reported) {  // EPA.c:636-651
+          const uint32_t word = W.fv[report_face];
+          const int a = word & 0xff, b = (word >> 8) & 0xff, c = (word >> 16) & 0xff;
+          T a0, a1, a2;
+          origin_barycentric(work_vertex(W, a), work_vertex(W, b), work_vertex(W, c), a0, a1, a2);
+          const V3<T> pa = load3(A.c, W.src1[a]), pb = load3(A.c, W.src1[b]), pc = load3(A.c, W.src1[c]);
+          const V3<T> qa = load3(B.c, W.src2[a]), qb = load3(B.c, W.src2[b]), qc = load3(B.c, W.src2[c]);
+          sp->witnesses[0][0] = add_rn(add_rn(mul_rn(pa.x, a0), mul_rn(pb.x, a1)), mul_rn(pc.x, a2));
+          sp->witnesses[0][1] = add_rn(add_rn(mul_rn(pa.y, a0), mul_rn(pb.y, a1)), mul_rn(pc.y, a2));
+          sp->witnesses[0][2] = add_rn(add_rn(mul_rn(pa.z, a0), mul_rn(pb.z, a1)), mul_rn(pc.z, a2));
+          sp->witnesses[1][0] = add_rn(add_rn(mul_rn(qa.x, a0), mul_rn(qb.x, a1)), mul_rn(qc.x, a2));
+          sp->witnesses[1][1] = add_rn(add_rn(mul_rn(qa.y, a0), mul_rn(qb.y, a1)), mul_rn(qc.y, a2));
+          sp->witnesses[1][2] = add_rn(add_rn(mul_rn(qa.z, a0), mul_rn(qb.z, a1)), mul_rn(qc.z, a2));
+          nrm_out[0] = W.nx[report_face];
+          nrm_out[1] = W.ny[report_face];
+          nrm_out[2] = W.nz[report_face];
+          distances[pair] = -report_d;
+        }
+      }
+      phase = kIdle;
+    }
+  }
+}
+
+}  // namespace ogjk

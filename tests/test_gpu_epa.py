@@ -103,3 +103,25 @@ def test_grid_cubes_and_spheres(pkg, oracle_mod, dtype):
         got = eng.compute_gjk_epa(bd1, bd2)
         s, d = orc.gjk(a[None], b[None])
         _compare(dtype, got, orc.epa(a[None], b[None], s, d))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("nverts,spread", [(32, 1.0), (64, 2.0), (200, 1.5), (8, 0.5)])
+def test_group_kernel_matches_oracle(pkg, oracle_mod, dtype, nverts, spread):
+    """the opt-in sub-warp group EPA kernel (OGJK_EPA_KERNEL=group, epa_group.cuh); needs >= 8192 pairs to be taken"""
+    import os
+    n = 12000 if nverts <= 64 else 9000
+    a, b = pkg.workloads.random_pairs(n, nverts, spread, seed=123, dtype=dtype)
+    eng = pkg.Engine(dtype)
+    bd1, _k1 = pkg.make_polytopes(a)
+    bd2, _k2 = pkg.make_polytopes(b)
+    saved = os.environ.get("OGJK_EPA_KERNEL")
+    os.environ["OGJK_EPA_KERNEL"] = "group"
+    try:
+        got = eng.compute_gjk_epa(bd1, bd2)
+    finally:
+        if saved is None:
+            os.environ.pop("OGJK_EPA_KERNEL", None)
+        else:
+            os.environ["OGJK_EPA_KERNEL"] = saved
+    _compare(dtype, got, _oracle_gjk_epa(oracle_mod, dtype, a, b))
