@@ -250,6 +250,76 @@ OGJK_D void support_slots_both(const float* b1, const float* b2, int nv, const V
   recover_support(b2, c2, bg2, best2, D2, v, sup2, idx2);
 }
 
+// ---- per-warp ticket feed ------------------------------------------------------------------------------------------
+// Pair indices are handed out through one global counter, 32 at a time per warp.  A warp holds the chunk it is
+// consuming and prepares the NEXT one in the background, in three steps spread over successive calls so that neither
+// the atomic's round trip nor -- for indexed batches (pairs = gkCollisionPair records into one polytope pool,
+// reference openGJK.cu:1451-1476) -- the load of the chunk's records ever sits between a finished pair and its
+// refill: (1) a quarter into the current chunk lane 0 issues the atomic, (2) once 20 tickets are gone its result is
+// broadcast and lane l loads the record of ticket nbase + l into registers, (3) when the chunk runs out the
+// registers become the current chunk.  `take` serves the lanes that raise `want` in ticket order; a request that
+// straddles two chunks is served in two passes.
+constexpr unsigned kTicketChunk = 32;
+struct TicketFeed {
+  unsigned base, next;  // current chunk [base, base + 32), next ticket to hand out
+  unsigned nbase, raw;  // the chunk being prepared: its first ticket (valid at stage 2), lane 0's atomic result
+  int stage;            // 0 nothing requested, 1 atomic issued, 2 nbase + records requested
+  int c1, c2, n1, n2;   // this lane's record of the current / next chunk (indexed batches)
+
+  OGJK_D void request(unsigned* ticket, int lane) {
+    if (lane == 0) raw = atomicAdd(ticket, kTicketChunk);
+    stage = 1;
+  }
+  OGJK_D void fetch(const CollisionPair* __restrict__ pairs, unsigned n, int lane) {
+    nbase = __shfl_sync(0xffffffffu, raw, 0);
+    n1 = n2 = 0;
+    if (pairs && nbase + lane < n) {
+      const CollisionPair pr = pairs[nbase + lane];
+      n1 = pr.idx1;
+      n2 = pr.idx2;
+    }
+    stage = 2;
+  }
+  OGJK_D void swap_in(unsigned* ticket, const CollisionPair* __restrict__ pairs, unsigned n, int lane) {
+    if (stage == 0) request(ticket, lane);
+    if (stage == 1) fetch(pairs, n, lane);
+    base = next = nbase;
+    c1 = n1;
+    c2 = n2;
+    stage = 0;
+  }
+  OGJK_D void init(unsigned* ticket, const CollisionPair* __restrict__ pairs, unsigned n, int lane) {
+    base = next = nbase = raw = 0;
+    c1 = c2 = n1 = n2 = 0;
+    stage = 0;
+    swap_in(ticket, pairs, n, lane);
+  }
+  // One pass: serves up to `avail` requesting lanes.  Returns true for a served lane and sets its ticket `t` and
+  // polytope indices (i1, i2) -- (t, t) for dense batches.  Call from all 32 lanes; repeat while lanes still want.
+  OGJK_D bool take(bool want, unsigned* ticket, const CollisionPair* __restrict__ pairs, unsigned n, int lane,
+                   unsigned& t, int& i1, int& i2) {
+    const unsigned wm = __ballot_sync(0xffffffffu, want);
+    if (!wm) return false;
+    const unsigned used = next - base;
+    if (stage == 0 && used >= 8) request(ticket, lane);
+    else if (stage == 1 && used >= 20) fetch(pairs, n, lane);
+    if (used == kTicketChunk) swap_in(ticket, pairs, n, lane);
+    const unsigned avail = base + kTicketChunk - next, cnt = __popc(wm);
+    const unsigned r = __popc(wm & ((1u << lane) - 1u));
+    const bool served = want && r < avail;
+    const unsigned mine = next + r;
+    const int src = (int)((mine - base) & 31u);
+    const int r1 = __shfl_sync(0xffffffffu, c1, src), r2 = __shfl_sync(0xffffffffu, c2, src);
+    if (served) {
+      t = mine;
+      i1 = pairs ? r1 : (int)mine;
+      i2 = pairs ? r2 : (int)mine;
+    }
+    next += cnt < avail ? cnt : avail;
+    return served;
+  }
+};
+
 struct SlotFetch {
   const float* b1;
   const float* b2;
@@ -260,7 +330,6 @@ struct SlotFetch {
 };
 
 constexpr int kSlotThreads = 128;
-constexpr int kTicketChunk = 64;
 constexpr uint32_t kSlotTableBytes = (kUnifiedSize * 2u + 15u) & ~15u;
 constexpr uint32_t kSlotFixedBytes = kSlotThreads * 8u + kSlotTableBytes;  // mbarriers + table
 constexpr uint32_t kSlotPadBytes = 96;  // look-ahead loads of the last slot stay inside the allocation
@@ -279,7 +348,7 @@ __global__ void __launch_bounds__(kSlotThreads)
 gjk_slots_kernel(const float* __restrict__ coord1, const float* __restrict__ coord2, int nv1, int nv2,
                  SimplexT<float>* __restrict__ simplices, float* __restrict__ distances, unsigned n,
                  const uint16_t* __restrict__ utab_g, unsigned* __restrict__ ticket, unsigned prefetch_ahead,
-                 unsigned zero) {
+                 unsigned zero, const CollisionPair* __restrict__ pairs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t sbytes = slot_bytes(nv1, nv2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // one mbarrier per thread
@@ -303,45 +372,28 @@ gjk_slots_kernel(const float* __restrict__ coord1, const float* __restrict__ coo
   int state = kNeedWork;
   uint32_t parity = 0;
   unsigned pair = 0;
-  unsigned tk_next = 0, tk_end = 0;  // this warp's reserved ticket range (warp-uniform)
+  TicketFeed feed;
+  feed.init(ticket, pairs, n, lane);
   GjkState<float> g;
+  (void)prefetch_ahead;
 
   for (;;) {
-    // ---- hand out work: per-warp ticket chunks ---------------------------------------------------------------
-    const unsigned want = __ballot_sync(0xffffffffu, state == kNeedWork);
-    if (want) {
-      const unsigned cnt = __popc(want), avail = tk_end - tk_next;
-      unsigned nb = 0;
-      if (cnt > avail) {
-        if (lane == 0) nb = atomicAdd(ticket, (unsigned)kTicketChunk);
-        nb = __shfl_sync(0xffffffffu, nb, 0);
-        if (prefetch_ahead) {  // the chunk `prefetch_ahead` pairs further on: two pairs per lane, contiguous in HBM
-          const unsigned long long p = (unsigned long long)nb + prefetch_ahead + 2u * lane;
-          if (p + 2 <= n) {
-            tma_prefetch_l2(coord1 + p * nv1 * 3, 2u * bytes1);
-            tma_prefetch_l2(coord2 + p * nv2 * 3, 2u * bytes2);
-          }
-        }
-      }
-      if (state == kNeedWork) {
-        const unsigned r = __popc(want & ((1u << lane) - 1u));
-        const unsigned t = r < avail ? tk_next + r : nb + (r - avail);
+    // ---- hand out work (two passes: a request may straddle two ticket chunks) --------------------------------------
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      unsigned t = 0;
+      int i1 = 0, i2 = 0;
+      if (feed.take(state == kNeedWork, ticket, pairs, n, lane, t, i1, i2)) {
         if (t < n) {
           pair = t;
           fence_proxy_async();  // this thread's earlier generic-proxy reads of the slot precede the async writes
           mbar_arrive_expect_tx(bar, bytes1 + bytes2);
-          tma_bulk_load(dst1, coord1 + (size_t)t * nv1 * 3, bytes1, bar);
-          tma_bulk_load(dst2, coord2 + (size_t)t * nv2 * 3, bytes2, bar);
+          tma_bulk_load(dst1, coord1 + (size_t)i1 * nv1 * 3, bytes1, bar);
+          tma_bulk_load(dst2, coord2 + (size_t)i2 * nv2 * 3, bytes2, bar);
           state = kLoading;
         } else {
           state = kDone;
         }
-      }
-      if (cnt > avail) {
-        tk_next = nb + (cnt - avail);
-        tk_end = nb + kTicketChunk;
-      } else {
-        tk_next += cnt;
       }
     }
     if (__all_sync(0xffffffffu, state == kDone)) break;
@@ -437,12 +489,15 @@ struct RecordFetch {  // vertex "index" = original simplex slot in bits 30..31 (
 // the two lanes of a pair each scan ONE body and exchange the support points with a shuffle, everything else is
 // evaluated redundantly on both -- twice the warps for the same shared memory, so each scheduler has a second warp to
 // issue from while the first waits on a dependency.
-template <int CW, int LP, bool EQ>
+// IDX: pairs are gkCollisionPair records into one pool (ticket feed with record prefetch); otherwise pair t is
+// (coord1[t], coord2[t]) and the loader draws plain ticket ranges.
+template <int CW, int LP, bool EQ, bool IDX>
 __global__ void __launch_bounds__((CW + 2) * 32)
 gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ coord2, int nv1, int nv2,
                     SimplexT<float>* __restrict__ simplices, float* __restrict__ distances, unsigned n,
                     const uint16_t* __restrict__ utab_g, unsigned* __restrict__ ticket, unsigned zero,
-                    float* __restrict__ normals, int* __restrict__ epa_queue, int* __restrict__ epa_count) {
+                    float* __restrict__ normals, int* __restrict__ epa_queue, int* __restrict__ epa_count,
+                    const CollisionPair* __restrict__ pairs) {
   constexpr int kCompute = CW * 32;
   constexpr int kSlots = kCompute / LP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -609,46 +664,66 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
     }
   } else if (warp == CW) {
     // ================================================ loader =================================================
-    unsigned tk_next = 0, tk_end = 0;  // reserved ticket range (warp-uniform)
+    TicketFeed feed;
+    if (IDX) feed.init(ticket, pairs, n, lane);
+    unsigned tk_next = 0, tk_end = 0;  // dense batches: reserved ticket range (warp-uniform), 64 per atomic
     unsigned exited = 0;               // bit j: slot lane + 32 j has been told to exit
     for (;;) {
       bool any = false;
 #pragma unroll
       for (int j = 0; j < kSlots / 32; ++j) {
         const int s = lane + 32 * j;
-        const bool want = !((exited >> j) & 1u) && ld_vol(&ctrl[s]) == kSlotFree;
+        bool want = !((exited >> j) & 1u) && ld_vol(&ctrl[s]) == kSlotFree;
         const unsigned wm = __ballot_sync(0xffffffffu, want);
-        if (!wm) continue;
+        if (!wm) continue;  // keep the idle polling loop light: it shares a scheduler with a compute warp
         any = true;
-        const unsigned cnt = __popc(wm), avail = tk_end - tk_next;
-        unsigned nb = 0;
-        if (cnt > avail) {
-          if (lane == 0) nb = atomicAdd(ticket, (unsigned)kTicketChunk);
-          nb = __shfl_sync(0xffffffffu, nb, 0);
-        }
-        if (want) {
-          const unsigned r = __popc(wm & ((1u << lane) - 1u));
-          const unsigned t = r < avail ? tk_next + r : nb + (r - avail);
-          if (t < n) {
-            __threadfence_block();  // the owner's last reads of the slot happened before it flagged FREE
-            pair_of[s] = t;
-            st_vol(&ctrl[s], kSlotBusy);
-            const uint32_t bar = smem_addr(&bars[s]);
-            const uint32_t dst1 = smem_addr(slots + (size_t)s * sbytes), dst2 = dst1 + lay.body2;
-            fence_proxy_async();
-            mbar_arrive_expect_tx(bar, bytes1 + bytes2);  // release: pair_of is visible to the waiting thread
-            tma_bulk_load(dst1, coord1 + (size_t)t * nv1 * 3, bytes1, bar);
-            tma_bulk_load(dst2, coord2 + (size_t)t * nv2 * 3, bytes2, bar);
-          } else {
-            st_vol(&ctrl[s], kSlotExit);
-            exited |= 1u << j;
+        unsigned nb = 0, avail = 0;
+        if (!IDX) {
+          avail = tk_end - tk_next;
+          if (__popc(wm) > avail) {
+            if (lane == 0) nb = atomicAdd(ticket, 64u);
+            nb = __shfl_sync(0xffffffffu, nb, 0);
           }
         }
-        if (cnt > avail) {
-          tk_next = nb + (cnt - avail);
-          tk_end = nb + kTicketChunk;
-        } else {
-          tk_next += cnt;
+#pragma unroll 1
+        for (int pass = 0; pass < (IDX ? 2 : 1); ++pass) {
+          unsigned t = 0;
+          int i1 = 0, i2 = 0;
+          bool served;
+          if (IDX) {
+            served = feed.take(want, ticket, pairs, n, lane, t, i1, i2);
+          } else {
+            const unsigned r = __popc(wm & ((1u << lane) - 1u));
+            t = r < avail ? tk_next + r : nb + (r - avail);
+            i1 = i2 = (int)t;
+            served = want;
+          }
+          if (served) {
+            want = false;
+            if (t < n) {
+              __threadfence_block();  // the owner's last reads of the slot happened before it flagged FREE
+              pair_of[s] = t;
+              st_vol(&ctrl[s], kSlotBusy);
+              const uint32_t bar = smem_addr(&bars[s]);
+              const uint32_t dst1 = smem_addr(slots + (size_t)s * sbytes), dst2 = dst1 + lay.body2;
+              fence_proxy_async();
+              mbar_arrive_expect_tx(bar, bytes1 + bytes2);  // release: pair_of is visible to the waiting thread
+              tma_bulk_load(dst1, coord1 + (size_t)i1 * nv1 * 3, bytes1, bar);
+              tma_bulk_load(dst2, coord2 + (size_t)i2 * nv2 * 3, bytes2, bar);
+            } else {
+              st_vol(&ctrl[s], kSlotExit);
+              exited |= 1u << j;
+            }
+          }
+        }
+        if (!IDX) {
+          const unsigned cnt = __popc(wm);
+          if (cnt > avail) {
+            tk_next = nb + (cnt - avail);
+            tk_end = nb + 64u;
+          } else {
+            tk_next += cnt;
+          }
         }
       }
       if (__all_sync(0xffffffffu, exited == (1u << (kSlots / 32)) - 1u)) break;

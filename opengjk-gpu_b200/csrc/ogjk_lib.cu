@@ -169,7 +169,8 @@ unsigned slots_prefetch_ahead() {
   return v < 0 ? 0u : (unsigned)v;
 }
 
-int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist) {
+int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist,
+                     const CollisionPair* pairs = nullptr) {
   int dev = 0, sms = 0, per_sm = 0;
   OGJK_CK(cudaGetDevice(&dev));
   const uint16_t* utab = nullptr;
@@ -187,7 +188,7 @@ int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, 
   if (grid > need) grid = need;
   OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
   kern<<<(unsigned)grid, kSlotThreads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab, t_ticket[dev],
-                                                         slots_prefetch_ahead(), 0u);
+                                                         slots_prefetch_ahead(), 0u, pairs);
   return finish_launch("gjk slots kernel");
 }
 
@@ -213,7 +214,7 @@ int ws_compute_warps(int nv1, int nv2) {
 }
 template <int CW, int LP>
 int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp,
-                           float* dist, float* nrm, int* queue, int* count) {
+                           float* dist, float* nrm, int* queue, int* count, const CollisionPair* pairs) {
   int dev = 0, sms = 0, per_sm = 0;
   OGJK_CK(cudaGetDevice(&dev));
   const uint16_t* utab = nullptr;
@@ -222,7 +223,9 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float
   constexpr int nslots = CW * 32 / LP;
   const size_t smem = (size_t)ws_fixed_bytes(nslots) + kSlotPadBytes + (size_t)nslots * ws_slot_layout(nv1, nv2, LP).stride;
   constexpr int threads = (CW + 2) * 32;
-  auto kern = (LP == 1 && nv1 == nv2) ? gjk_slots_ws_kernel<CW, LP, true> : gjk_slots_ws_kernel<CW, LP, false>;
+  auto kern = pairs ? gjk_slots_ws_kernel<CW, LP, LP == 1, true>  // one pool: equal vertex counts by construction
+                    : (LP == 1 && nv1 == nv2) ? gjk_slots_ws_kernel<CW, LP, true, false>
+                                              : gjk_slots_ws_kernel<CW, LP, false, false>;
   OGJK_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -232,16 +235,16 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float
   if (grid > need) grid = need;
   OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
   kern<<<(unsigned)grid, threads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab, t_ticket[dev], 0u,
-                                                    nrm, queue, count);
+                                                    nrm, queue, count, pairs);
   return finish_launch("gjk slots (warp-specialised) kernel");
 }
 int launch_gjk_slots_ws(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist,
-                        float* nrm, int* queue, int* count) {
+                        float* nrm, int* queue, int* count, const CollisionPair* pairs = nullptr) {
   int lp = 1;
   const int cw = ws_config(nv1, nv2, &lp);
-  if (cw == 8 && lp == 1) return launch_gjk_slots_ws_cw<8, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count);
-  if (cw == 8 && lp == 2) return launch_gjk_slots_ws_cw<8, 2>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count);
-  if (cw == 4) return launch_gjk_slots_ws_cw<4, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count);
+  if (cw == 8 && lp == 1) return launch_gjk_slots_ws_cw<8, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  if (cw == 8 && lp == 2) return launch_gjk_slots_ws_cw<8, 2>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  if (cw == 4) return launch_gjk_slots_ws_cw<4, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
   return 1;
 }
 
@@ -429,6 +432,91 @@ int launch_gjk_epa_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, Si
   return rc;
 }
 
+// ---- indexed batches over a uniform pool ------------------------------------------------------------------------
+// Pools uploaded by this library (allocate_indexed_device, the host-level *_indexed calls) are remembered when every
+// polytope has the same vertex count (a multiple of 4): their coordinates then lie densely in the blob, pair t's two
+// bodies are pool[idx1] and pool[idx2], and the slot kernels can be fed from the gkCollisionPair list.  Descriptor
+// arrays built by the caller (the visualiser does that) are not in the registry and take the general kernel.
+constexpr int kGjkStage = 1, kEpaStage = 2;  // = Stage::kGjk, Stage::kEpa below
+struct PoolInfo {
+  const void* coords;
+  int nv;
+  int count;
+};
+std::mutex g_pool_mutex;
+std::vector<std::pair<const void*, PoolInfo>> g_pools;  // keyed by the device descriptor pointer
+void register_pool(const void* d_desc, const void* d_coords, int nv, int count) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  g_pools.push_back({d_desc, PoolInfo{d_coords, nv, count}});
+}
+void unregister_pool(const void* d_desc) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  for (size_t i = 0; i < g_pools.size(); ++i)
+    if (g_pools[i].first == d_desc) {
+      g_pools.erase(g_pools.begin() + i);
+      return;
+    }
+}
+bool lookup_pool(const void* d_desc, PoolInfo* out) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  for (const auto& p : g_pools)
+    if (p.first == d_desc) {
+      *out = p.second;
+      return true;
+    }
+  return false;
+}
+
+// GJK (and optionally the fused EPA gate + EPA) over `pairs` into a uniform fp32 pool.  Returns 1 when the batch does
+// not qualify for the slot kernels.
+template <typename T>
+int launch_indexed_uniform(int, const PoolInfo&, const CollisionPair*, const PolytopeT<T>*, SimplexT<T>*, T*, T*, int) {
+  return 1;
+}
+template <>
+int launch_indexed_uniform<float>(int n, const PoolInfo& pool, const CollisionPair* d_pairs,
+                                  const PolytopeT<float>* d_desc, SimplexT<float>* simp, float* dist, float* nrm,
+                                  int stages) {
+  const int nv = pool.nv;
+  const float* base = (const float*)pool.coords;
+  const int force = forced_kernel();
+  if (nv <= 0 || nv % 4 || n < 32768 || force == 2 || force == 3 || !(stages & kGjkStage)) return 1;
+  const bool ws = force == 4 || (force == 0 && use_ws_kernel(nv, nv));
+  const bool v2_fits = (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv, nv) <= 227u * 1024u;
+  if (!ws && !v2_fits) return 1;
+  if (ws && ws_compute_warps(nv, nv) == 0) return 1;
+  const bool epa = (stages & kEpaStage) != 0;
+  if (!epa) {
+    return ws ? launch_gjk_slots_ws(n, nv, base, nv, base, simp, dist, nullptr, nullptr, nullptr, d_pairs)
+              : launch_gjk_slots(n, nv, base, nv, base, simp, dist, d_pairs);
+  }
+  if (!nrm) return fail_msg("contact_normals must not be NULL on the device path");
+  IndexedSource<float> src{d_desc, d_pairs};
+  const bool sync_saved = t_sync;
+  t_sync = false;
+  int rc;
+  if (ws) {  // gate fused into the finisher warp
+    int* scratch = nullptr;
+    if ((rc = epa_scratch((size_t)n + 2, &scratch))) {
+      t_sync = sync_saved;
+      return rc;
+    }
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * sizeof(int), t_stream);
+    if (e != cudaSuccess) {
+      t_sync = sync_saved;
+      return fail("cudaMemsetAsync", e);
+    }
+    rc = launch_gjk_slots_ws(n, nv, base, nv, base, simp, dist, nrm, scratch + 2, scratch, d_pairs);
+    t_sync = sync_saved;
+    if (!rc) rc = launch_epa_queue<float, IndexedSource<float>>(src, n, simp, dist, nrm, scratch + 2, scratch);
+    return rc;
+  }
+  rc = launch_gjk_slots(n, nv, base, nv, base, simp, dist, d_pairs);
+  t_sync = sync_saved;
+  if (!rc) rc = launch_epa<float>(src, n, simp, dist, nrm);
+  return rc;
+}
+
 // numpoints of the first descriptor of a device array (vertex-count hint for lane selection)
 template <typename T>
 int peek_numpoints(const PolytopeT<T>* d_bd, int* nv) {
@@ -448,18 +536,22 @@ struct Flattened {
   PolytopeT<T>* d_desc = nullptr;
   T* d_coord = nullptr;
   long long max_nv = 0;
+  int uniform_nv = 0;  // > 0: every polytope has this many vertices (a multiple of 4), coordinates dense in the blob
 };
 
 template <typename T>
 int flatten_upload(int n, const PolytopeT<T>* bd, Flattened<T>& out) {
   size_t total = 0;
   long long max_nv = 0;
+  bool uniform = n > 0 && bd[0].numpoints % 4 == 0;
   const size_t align = 16 / sizeof(T);
   for (int i = 0; i < n; ++i) {
     if (bd[i].numpoints < 1 || !bd[i].coord) return fail_msg("polytope with no vertices");
     total += ((size_t)bd[i].numpoints * 3 + align - 1) / align * align;
     if (bd[i].numpoints > max_nv) max_nv = bd[i].numpoints;
+    if (bd[i].numpoints != bd[0].numpoints) uniform = false;
   }
+  out.uniform_nv = uniform ? bd[0].numpoints : 0;
   T* h_coord = nullptr;
   PolytopeT<T>* h_desc = nullptr;
   OGJK_CK(cudaMallocHost(&h_coord, total * sizeof(T)));
@@ -761,8 +853,14 @@ int run_indexed_host(int num_polytopes, int num_pairs, const PolytopeT<T>* polyt
     {
       SyncOverride nosync;
       IndexedSource<T> src{pool.d_desc, d_pairs};
-      if ((stages & kGjk) && (rc = launch_gjk_generic<T>(src, num_pairs, (int)pool.max_nv, d_simp, d_dist))) break;
-      if ((stages & kEpa) && (rc = launch_epa<T>(src, num_pairs, d_simp, d_dist, d_nrm))) break;
+      const PoolInfo info{pool.d_coord, pool.uniform_nv, num_polytopes};
+      rc = launch_indexed_uniform<T>(num_pairs, info, d_pairs, pool.d_desc, d_simp, d_dist, d_nrm, stages);
+      if (rc < 0 || (rc != 0 && rc != 1)) break;
+      if (rc == 1) {  // not a uniform fp32 pool / small batch: the general kernels
+        rc = 0;
+        if ((stages & kGjk) && (rc = launch_gjk_generic<T>(src, num_pairs, (int)pool.max_nv, d_simp, d_dist))) break;
+        if ((stages & kEpa) && (rc = launch_epa<T>(src, num_pairs, d_simp, d_dist, d_nrm))) break;
+      }
     }
     if ((e = cudaMemcpyAsync(simplices, d_simp, np * sizeof(SimplexT<T>), cudaMemcpyDeviceToHost, t_stream)) != cudaSuccess) { rc = fail("D2H simplices", e); break; }
     if ((e = cudaMemcpyAsync(distances, d_dist, np * sizeof(T), cudaMemcpyDeviceToHost, t_stream)) != cudaSuccess) { rc = fail("D2H distances", e); break; }
@@ -940,6 +1038,7 @@ long long ogjk_launch_count(int reset) {
     if (int rc = flatten_upload<REAL>(num_polytopes, (const PolytopeT<REAL>*)polytopes, pool)) return rc;              \
     *d_polytopes = pool.d_desc;                                                                                        \
     *d_coords = pool.d_coord;                                                                                          \
+    if (pool.uniform_nv > 0) register_pool(pool.d_desc, pool.d_coord, pool.uniform_nv, num_polytopes);                 \
     OGJK_CK(cudaMalloc(d_pairs, (size_t)max_pairs * sizeof(CollisionPair)));                                           \
     OGJK_CK(cudaMalloc(d_simplices, (size_t)max_pairs * sizeof(SimplexT<REAL>)));                                      \
     OGJK_CK(cudaMalloc((void**)d_distances, (size_t)max_pairs * sizeof(REAL)));                                        \
@@ -948,6 +1047,7 @@ long long ogjk_launch_count(int reset) {
   }                                                                                                                    \
   int ogjk_##P##_free_indexed_device(void* d_polytopes, REAL* d_coords, void* d_pairs, void* d_simplices,             \
                                      REAL* d_distances, REAL* d_contact_normals) {                                    \
+    unregister_pool(d_polytopes);                                                                                      \
     cudaFree(d_polytopes);                                                                                             \
     cudaFree(d_coords);                                                                                                \
     cudaFree(d_pairs);                                                                                                 \
@@ -972,6 +1072,13 @@ long long ogjk_launch_count(int reset) {
                                                          const void* d_pairs, void* d_simplices,                      \
                                                          REAL* d_distances) {                                         \
     if (num_pairs <= 0) return 0;                                                                                      \
+    PoolInfo info;                                                                                                     \
+    if (lookup_pool(d_polytopes, &info)) {                                                                             \
+      const int fast = launch_indexed_uniform<REAL>(num_pairs, info, (const CollisionPair*)d_pairs,                    \
+                                                    (const PolytopeT<REAL>*)d_polytopes, (SimplexT<REAL>*)d_simplices, \
+                                                    d_distances, nullptr, kGjkStage);                                  \
+      if (fast <= 0) return fast;                                                                                      \
+    }                                                                                                                  \
     int nv = 0;                                                                                                        \
     if (int rc = peek_numpoints<REAL>((const PolytopeT<REAL>*)d_polytopes, &nv)) return rc;                            \
     IndexedSource<REAL> src{(const PolytopeT<REAL>*)d_polytopes, (const CollisionPair*)d_pairs};                       \

@@ -116,3 +116,36 @@ def test_fused_gjk_epa_uniform_device(pkg, oracle_mod, force_kernel, nverts, spr
     assert np.array_equal(d_nrm.cpu().numpy(), nr)
     assert live_simplex_equal(d_simp.cpu().numpy().view(eng.sdtype), s)
     eng.set_stream(0)
+
+
+@pytest.mark.parametrize("kernel", ["auto", "slots", "slotsws"])
+@pytest.mark.parametrize("nverts", [32, 64])
+def test_indexed_uniform_pool_takes_slot_kernels(pkg, oracle_mod, force_kernel, kernel, nverts):
+    """BASELINE config 5 in small: uniform pool + gkCollisionPair list (broad-phase candidates) through the host-level
+    and device-level indexed entry points; >= 32768 pairs so that the slot kernels are fed from the pair list."""
+    npoly = 1500
+    pool, pairs = pkg.workloads.broadphase_pool(npoly, nverts, 45000, seed=17)
+    assert pairs.shape[0] >= 32768
+    off = np.arange(npoly + 1) * nverts
+    flat = pool.reshape(-1, 3)
+    orc = oracle_mod.Oracle("port", np.float32)
+    gs, gd, _ = orc.gjk_epa_indexed(flat, pairs, off, do_epa=False, nthreads=8)
+    es, ed, en = orc.gjk_epa_indexed(flat, pairs, off, nthreads=8)
+    eng = pkg.Engine(np.float32)
+    desc, _keep = pkg.make_polytopes(pool)
+    force_kernel(kernel)
+    s, d = eng.compute_minimum_distance_indexed(desc, pairs)
+    assert np.array_equal(d, gd) and live_simplex_equal(s, gs)
+    s3, d3, n3 = eng.compute_gjk_epa_indexed(desc, pairs)
+    assert np.array_equal(d3, ed) and np.array_equal(n3, en) and live_simplex_equal(s3, es)
+    dp, dc, dpairs, dsimp, ddist, dnrm = eng.allocate_indexed_device(desc, len(pairs))
+    try:
+        eng.upload_pairs_device(pairs, dpairs)
+        eng.compute_minimum_distance_indexed_device(len(pairs), dp, dpairs, dsimp, ddist)
+        s4, d4 = eng.copy_results_from_device(len(pairs), dsimp, ddist)
+        assert np.array_equal(d4, gd) and live_simplex_equal(s4, gs)
+        eng.compute_epa_indexed_device(len(pairs), dp, dpairs, dsimp, ddist, dnrm)
+        s5, d5 = eng.copy_results_from_device(len(pairs), dsimp, ddist)
+        assert np.array_equal(d5, ed) and live_simplex_equal(s5, es)
+    finally:
+        eng.free_indexed_device(dp, dc, dpairs, dsimp, ddist, dnrm)
