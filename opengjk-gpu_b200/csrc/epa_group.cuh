@@ -164,7 +164,7 @@ struct EpaGroupConfig {
 };
 
 template <typename T, int G, typename Source>
-__global__ void __launch_bounds__(EpaGroupConfig<T>::kThreads)
+__global__ void __launch_bounds__(EpaGroupConfig<T>::kThreads, (G == 16 && sizeof(T) == 4) ? 20 : 1)
 epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
                  T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char epa_smem[];

@@ -497,7 +497,7 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
                     SimplexT<float>* __restrict__ simplices, float* __restrict__ distances, unsigned n,
                     const uint16_t* __restrict__ utab_g, unsigned* __restrict__ ticket, unsigned zero,
                     float* __restrict__ normals, int* __restrict__ epa_queue, int* __restrict__ epa_count,
-                    const CollisionPair* __restrict__ pairs) {
+                    const CollisionPair* __restrict__ pairs, unsigned dense_chunk) {
   constexpr int kCompute = CW * 32;
   constexpr int kSlots = kCompute / LP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -666,7 +666,7 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
     // ================================================ loader =================================================
     TicketFeed feed;
     if (IDX) feed.init(ticket, pairs, n, lane);
-    unsigned tk_next = 0, tk_end = 0;  // dense batches: reserved ticket range (warp-uniform), 64 per atomic
+    unsigned tk_next = 0, tk_end = 0;  // dense batches: reserved ticket range (warp-uniform), dense_chunk per atomic
     unsigned exited = 0;               // bit j: slot lane + 32 j has been told to exit
     for (;;) {
       bool any = false;
@@ -681,7 +681,7 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
         if (!IDX) {
           avail = tk_end - tk_next;
           if (__popc(wm) > avail) {
-            if (lane == 0) nb = atomicAdd(ticket, 64u);
+            if (lane == 0) nb = atomicAdd(ticket, dense_chunk);
             nb = __shfl_sync(0xffffffffu, nb, 0);
           }
         }
@@ -720,7 +720,7 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
           const unsigned cnt = __popc(wm);
           if (cnt > avail) {
             tk_next = nb + (cnt - avail);
-            tk_end = nb + 64u;
+            tk_end = nb + dense_chunk;
           } else {
             tk_next += cnt;
           }

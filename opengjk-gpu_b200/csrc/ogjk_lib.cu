@@ -192,6 +192,13 @@ int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, 
   return finish_launch("gjk slots kernel");
 }
 
+// tickets per atomic of the ws loader on dense batches (>= 32); development override OGJK_WS_CHUNK
+unsigned ws_dense_chunk() {
+  const char* e = getenv("OGJK_WS_CHUNK");
+  const int v = e ? atoi(e) : 64;
+  return v < 32 ? 32u : (unsigned)v;
+}
+
 // warp-specialised slot kernel.  Configurations (compute warps, lanes per pair): (8,1) when 256 slots fit an SM;
 // otherwise (8,2) -- 128 slots, two lanes per pair -- or (4,1).  normals/queue/count non-null = fused EPA gate.
 // development override: OGJK_WS_LP=1|2 picks between (4,1) and (8,2) for the 128-slot case.
@@ -235,7 +242,7 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float
   if (grid > need) grid = need;
   OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
   kern<<<(unsigned)grid, threads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab, t_ticket[dev], 0u,
-                                                    nrm, queue, count, pairs);
+                                                    nrm, queue, count, pairs, ws_dense_chunk());
   return finish_launch("gjk slots (warp-specialised) kernel");
 }
 int launch_gjk_slots_ws(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist,
@@ -322,6 +329,24 @@ int epa_scratch(size_t ints, int** out) {
   return 0;
 }
 
+template <typename T, int G, typename Source>
+int launch_epa_group(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distances, T* d_normals, const int* queue,
+                     int* counters, int sms) {
+  constexpr int threads = EpaGroupConfig<T>::kThreads;
+  constexpr int groups = threads / G;
+  const size_t smem = (size_t)groups * sizeof(EpaWork<T>);
+  int per_sm = 0;
+  auto kern = epa_group_kernel<T, G, Source>;
+  OGJK_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)sms * per_sm;
+  const long long need = ((long long)n + groups - 1) / groups;
+  if (grid > need) grid = need;
+  kern<<<(unsigned)grid, threads, smem, t_stream>>>(src, d_simplices, d_distances, d_normals, queue, counters);
+  return finish_launch("epa group kernel");
+}
+
 // persistent EPA over a device-side queue of colliding pairs (counters[0] = queued pairs, counters[1] = ticket).
 // Default: one warp per pair.  OGJK_EPA_KERNEL=group selects the sub-warp group kernel (8 lanes per pair, four pairs per
 // warp in lock step, epa_group.cuh): 38 % fewer warp instructions per pair but, at 11 warps per SM, latency-bound --
@@ -344,19 +369,9 @@ int launch_epa_queue(const Source& src, int n, SimplexT<T>* d_simplices, T* d_di
                                                                           queue, counters);
     return finish_launch("epa kernel");
   }
-  constexpr int G = EpaGroupConfig<T>::kGroup;
-  constexpr int threads = EpaGroupConfig<T>::kThreads;
-  constexpr int groups = threads / G;
-  const size_t smem = (size_t)groups * sizeof(EpaWork<T>);
-  auto kern = epa_group_kernel<T, G, Source>;
-  OGJK_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-  if (per_sm < 1) per_sm = 1;
-  long long grid = (long long)sms * per_sm;
-  const long long need = ((long long)n + groups - 1) / groups;
-  if (grid > need) grid = need;
-  kern<<<(unsigned)grid, threads, smem, t_stream>>>(src, d_simplices, d_distances, d_normals, queue, counters);
-  return finish_launch("epa group kernel");
+  const char* eg = getenv("OGJK_EPA_GROUP");  // development: lanes per pair of the group kernel (8 or 16)
+  if (eg && atoi(eg) == 16) return launch_epa_group<T, 16, Source>(src, n, d_simplices, d_distances, d_normals, queue, counters, sms);
+  return launch_epa_group<T, 8, Source>(src, n, d_simplices, d_distances, d_normals, queue, counters, sms);
 }
 
 // EPA launch: small batches get one warp per pair; large ones go through gate + compaction + a persistent
@@ -647,15 +662,16 @@ int pool_streams(DevicePool& p, size_t chunks) {
 }
 
 // Is the descriptor array a dense uniform batch, i.e. numpoints identical and coord[i] = coord[0] + i*nv*3 ?
+// Checked for descriptors [lo, hi) against descriptor 0: the host path validates chunk by chunk, right before it
+// queues the chunk's copies, so that walking 64 MB of descriptors hides behind the PCIe transfer instead of preceding it.
 template <typename T>
-bool dense_uniform(int n, const PolytopeT<T>* bd, int* nv_out) {
+bool dense_uniform_range(const PolytopeT<T>* bd, size_t lo, size_t hi) {
   const int nv = bd[0].numpoints;
   const T* base = bd[0].coord;
   if (nv < 1 || !base) return false;
   const size_t stride = (size_t)nv * 3;
-  for (int i = 0; i < n; ++i)
-    if (bd[i].numpoints != nv || bd[i].coord != base + (size_t)i * stride) return false;
-  *nv_out = nv;
+  for (size_t i = lo; i < hi; ++i)
+    if (bd[i].numpoints != nv || bd[i].coord != base + i * stride) return false;
   return true;
 }
 
@@ -671,8 +687,12 @@ struct StreamOverride {  // run the launch helpers on one of the pool's streams
 template <typename T>
 int run_pairs_host_dense(int n, const PolytopeT<T>* bd1, const PolytopeT<T>* bd2, SimplexT<T>* simplices,
                          T* distances, T* normals, int stages) {
-  int nv1 = 0, nv2 = 0;
-  if (!dense_uniform(n, bd1, &nv1) || !dense_uniform(n, bd2, &nv2)) return 1;
+  // a cheap look at both ends decides whether to try; every chunk is validated in full before it is queued
+  const size_t probe = n < 64 ? (size_t)n : 64;
+  if (!dense_uniform_range(bd1, 0, probe) || !dense_uniform_range(bd2, 0, probe) ||
+      !dense_uniform_range(bd1, (size_t)n - probe, (size_t)n) || !dense_uniform_range(bd2, (size_t)n - probe, (size_t)n))
+    return 1;
+  const int nv1 = bd1[0].numpoints, nv2 = bd2[0].numpoints;
   if (nv1 % 4 || nv2 % 4 || nv1 > 256 || nv2 > 256) return 1;
   if ((((uintptr_t)bd1[0].coord | (uintptr_t)bd2[0].coord) & 15u) != 0) return 1;
   int dev = 0;
@@ -704,6 +724,13 @@ int run_pairs_host_dense(int n, const PolytopeT<T>* bd1, const PolytopeT<T>* bd2
   for (size_t k = 0; k < chunks; ++k) {
     const size_t lo = k * chunk_pairs;
     const int m = (int)(((size_t)n - lo) < chunk_pairs ? ((size_t)n - lo) : chunk_pairs);
+    if (!dense_uniform_range(bd1, lo, lo + m) || !dense_uniform_range(bd2, lo, lo + m)) {
+      // not a dense batch after all: drain what was queued and let the general path redo the whole call
+      cudaStreamSynchronize(P.s_copy);
+      cudaStreamSynchronize(P.s_comp);
+      cudaStreamSynchronize(P.s_out);
+      return 1;
+    }
     OGJK_CK(cudaMemcpyAsync(d_c1 + lo * nv1 * 3, h_c1 + lo * nv1 * 3, (size_t)m * nv1 * 3 * sizeof(T),
                             cudaMemcpyHostToDevice, P.s_copy));
     OGJK_CK(cudaMemcpyAsync(d_c2 + lo * nv2 * 3, h_c2 + lo * nv2 * 3, (size_t)m * nv2 * 3 * sizeof(T),

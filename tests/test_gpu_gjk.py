@@ -65,3 +65,28 @@ def test_empty_batch_is_noop(pkg):
     bd = np.zeros(0, dtype=eng.pdtype)
     simp, dist = eng.compute_minimum_distance(bd, bd)
     assert len(simp) == 0 and len(dist) == 0
+
+
+def test_almost_dense_batch_falls_back(pkg, oracle_mod):
+    """The host path streams dense uniform batches straight from the caller's arrays and validates the descriptors
+    chunk by chunk while copying; a batch that only LOOKS dense at both ends (one descriptor in the middle points
+    somewhere else, one has a different vertex count) must be detected mid-way and redone through the general path."""
+    dtype = np.float32
+    n, nv = 60000, 16
+    a, b = pkg.workloads.random_pairs(n, nv, 6.0, seed=808, dtype=dtype)
+    bd1, keep1 = pkg.make_polytopes(a)
+    bd2, keep2 = pkg.make_polytopes(b)
+    moved = np.ascontiguousarray(a[31000])          # same vertices, different address
+    bd1["coord"][31000] = moved.ctypes.data
+    short = np.ascontiguousarray(b[45000][:12])     # fewer vertices
+    bd2["coord"][45000] = short.ctypes.data
+    bd2["numpoints"][45000] = 12
+    eng = pkg.Engine(dtype)
+    simp, dist = eng.compute_minimum_distance(bd1, bd2)
+    orc = oracle_mod.Oracle("port", dtype)
+    os_, od = orc.gjk(a, b, nthreads=8)
+    ref_s, ref_d = orc.gjk(a[45000:45001], short[None], nthreads=1)
+    od[45000] = ref_d[0]
+    os_[45000] = ref_s[0]
+    assert np.array_equal(dist, od)
+    assert live_simplex_equal(simp, os_)
