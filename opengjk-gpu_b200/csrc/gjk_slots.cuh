@@ -528,7 +528,7 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
     ctrl[tid] = kSlotFree;
     pair_of[tid] = 0;
   }
-  if (tid < kRingRecords) ready[tid] = 0;
+  for (int i = tid; i < kRingRecords; i += (CW + 2) * 32) ready[i] = 0;
   if (tid < 4) ring_ctl[tid] = 0;
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   fence_proxy_async();

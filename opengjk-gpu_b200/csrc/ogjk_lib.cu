@@ -200,7 +200,7 @@ unsigned ws_dense_chunk() {
 }
 
 // warp-specialised slot kernel.  Configurations (compute warps, lanes per pair): (8,1) when 256 slots fit an SM;
-// otherwise (8,2) -- 128 slots, two lanes per pair -- or (4,1).  normals/queue/count non-null = fused EPA gate.
+// otherwise (8,2) -- 128 slots, two lanes per pair -- or (4,1); (2,1) = 64 slots for 65..~140 vertices per body.  normals/queue/count non-null = fused EPA gate.
 // development override: OGJK_WS_LP=1|2 picks between (4,1) and (8,2) for the 128-slot case.
 int ws_config(int nv1, int nv2, int* lp) {
   const size_t sb = slot_bytes(nv1, nv2);
@@ -213,6 +213,9 @@ int ws_config(int nv1, int nv2, int* lp) {
     return 8;
   }
   if (ws_fixed_bytes(128) + 128 * sb + kSlotPadBytes <= 227u * 1024u) return 4;
+  if (ws_fixed_bytes(64) + 64 * sb + kSlotPadBytes <= 227u * 1024u) return 2;  // 65..~140 vertices per body
+  // (one compute warp, 32 slots, up to ~270 vertices per body, was measured too: it loses to gjk_uniform_kernel,
+  //  2.0e8 against 3.1e8 pairs/s at 256 vertices, while two compute warps win, 7.3e8 against 4.7e8 at 96 vertices)
   return 0;
 }
 int ws_compute_warps(int nv1, int nv2) {
@@ -252,6 +255,7 @@ int launch_gjk_slots_ws(int n, int nv1, const float* c1, int nv2, const float* c
   if (cw == 8 && lp == 1) return launch_gjk_slots_ws_cw<8, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
   if (cw == 8 && lp == 2) return launch_gjk_slots_ws_cw<8, 2>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
   if (cw == 4) return launch_gjk_slots_ws_cw<4, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  if (cw == 2) return launch_gjk_slots_ws_cw<2, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
   return 1;
 }
 

@@ -42,7 +42,8 @@ def _device_batch(pkg, a, b, dtype=np.float32):
 
 @pytest.mark.parametrize("kernel", ["slots", "slotsws"])
 @pytest.mark.parametrize("nv1,nv2,spread", [(64, 64, 10.0), (32, 32, 1.0), (32, 32, 10.0), (8, 8, 10.0), (4, 4, 2.0),
-                                            (12, 20, 3.0), (64, 16, 6.0), (68, 68, 8.0), (16, 16, 0.5)])
+                                            (12, 20, 3.0), (64, 16, 6.0), (68, 68, 8.0), (16, 16, 0.5), (96, 96, 4.0), (128, 64, 5.0),
+                                            (140, 140, 10.0)])
 def test_slot_kernels_match_oracle(pkg, oracle_mod, force_kernel, kernel, nv1, nv2, spread):
     import torch
     n = 40000
