@@ -46,6 +46,16 @@ int ogjk_set_stream(void* stream);
 int ogjk_set_sync(int enabled);
 /* Number of kernels this library has launched on the calling thread since the last reset (bench accounting). */
 long long ogjk_launch_count(int reset);
+/* Uniform-grid broad phase on the device (the step before the hot path in the reference's caller:
+ * visualization/integrate_final_gjk.cu:467-570 insert/count/generate kernels, :916-1002 sim_broad_phase).
+ * d_pos_radius: num_objects x float4 = centre xyz + bounding radius.  An object lives in the cell
+ * floor((p + boundary) / cell_size) clamped to [0, grid_size); object i is paired with every j > i in the 27
+ * surrounding cells with |ci - cj|^2 < (ri + rj)^2 (fp32, unfused).  Pairs are written to d_pairs
+ * (gkCollisionPair[max_pairs]) grouped by i ascending, writes beyond max_pairs are dropped; *num_pairs receives the
+ * number of pairs found (compare with max_pairs to detect the clamp).  The list feeds
+ * ogjk_*_compute_minimum_distance_indexed_device / ogjk_*_compute_epa_indexed_device directly. */
+int ogjk_broadphase_pairs_device(int num_objects, const float* d_pos_radius, float cell_size, float boundary,
+                                 int grid_size, void* d_pairs, int max_pairs, long long* num_pairs);
 /* Per-stage device timing of the fused *_gjk_epa_uniform_device calls of this thread: while enabled every call
  * records CUDA events on the launching stream before GJK, between the stages and after EPA; ogjk_stage_times waits
  * for them, returns the summed GJK / EPA milliseconds and the number of calls, and resets the list. */

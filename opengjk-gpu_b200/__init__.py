@@ -145,6 +145,16 @@ class Engine:
             raise OgjkError(f"ogjk_stage_times failed ({rc}): {self.lib.ogjk_last_error().decode()}")
         return g.value, e.value, c.value
 
+    def broadphase_pairs_device(self, n, d_pos_radius, cell_size, boundary, grid_size, d_pairs, max_pairs) -> int:
+        """uniform-grid broad phase on device memory; returns the number of pairs found (may exceed max_pairs)"""
+        total = ctypes.c_longlong(0)
+        rc = self.lib.ogjk_broadphase_pairs_device(ctypes.c_int(n), _ptr(d_pos_radius), ctypes.c_float(cell_size),
+                                                   ctypes.c_float(boundary), ctypes.c_int(grid_size), _ptr(d_pairs),
+                                                   ctypes.c_int(max_pairs), ctypes.byref(total))
+        if rc != 0:
+            raise OgjkError(f"ogjk_broadphase_pairs_device failed ({rc}): {self.lib.ogjk_last_error().decode()}")
+        return int(total.value)
+
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.ogjk_launch_count(ctypes.c_int(int(reset))))
 

@@ -17,6 +17,7 @@
 #include "../../include/opengjk_b200.h"
 #include "epa_kernel.cuh"
 #include "epa_group.cuh"
+#include "broadphase.cuh"
 #include "gjk_generic.cuh"
 #include "gjk_tables.h"
 #include "gjk_slots.cuh"
@@ -908,6 +909,59 @@ int run_indexed_host(int num_polytopes, int num_pairs, const PolytopeT<T>* polyt
   return rc;
 }
 
+// ---- broad phase (reference visualization/integrate_final_gjk.cu:916-1002) -------------
+thread_local Scratch t_bp_scratch[kMaxDevices];
+
+int broadphase_pairs(int n, const float4* d_pos, float cell_size, float boundary, int grid_size, CollisionPair* d_pairs,
+                     int max_pairs, long long* num_pairs) {
+  if (num_pairs) *num_pairs = 0;
+  if (n <= 0) return 0;
+  if (!d_pos || (!d_pairs && max_pairs > 0)) return fail_msg("null argument");
+  if (!(cell_size > 0.0f) || grid_size < 1 || grid_size > 512) return fail_msg("bad grid (cell_size > 0, 1 <= grid_size <= 512)");
+  const size_t cells = (size_t)grid_size * grid_size * grid_size;
+  int dev = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail_msg("device ordinal out of range");
+  // obj_cell[n] | cell_count[cells] | cursor[cells] | cell_start[cells + 1] | cell_objs[n] | pair_counts[n] | pair_offsets[n + 1]
+  const size_t ints = 3 * (size_t)n + 3 * cells + (size_t)n + 2;
+  Scratch& sc = t_bp_scratch[dev];
+  if (sc.ints < ints) {
+    if (sc.ptr) cudaFree(sc.ptr);
+    sc.ptr = nullptr;
+    sc.ints = 0;
+    OGJK_CK(cudaMalloc(&sc.ptr, ints * sizeof(int)));
+    sc.ints = ints;
+  }
+  int* obj_cell = sc.ptr;
+  int* cell_count = obj_cell + n;
+  int* cursor = cell_count + cells;
+  int* cell_start = cursor + cells;
+  int* cell_objs = cell_start + cells + 1;
+  int* pair_counts = cell_objs + n;
+  int* pair_offsets = pair_counts + n;
+  OGJK_CK(cudaMemsetAsync(cell_count, 0, 2 * cells * sizeof(int), t_stream));  // counts + cursors
+  const unsigned tb = (unsigned)((n + 255) / 256);
+  const unsigned wb = (unsigned)(((long long)n * 32 + 255) / 256);
+  bp_histogram_kernel<<<tb, 256, 0, t_stream>>>(d_pos, n, cell_size, boundary, grid_size, obj_cell, cell_count);
+  bp_exclusive_scan_kernel<<<1, 1024, 0, t_stream>>>(cell_count, cell_start, (int)cells);
+  bp_fill_kernel<<<tb, 256, 0, t_stream>>>(obj_cell, n, cell_start, cursor, cell_objs);
+  bp_pairs_kernel<false><<<wb, 256, 0, t_stream>>>(d_pos, n, cell_size, boundary, grid_size, cell_start, cell_objs,
+                                                   pair_counts, nullptr, nullptr, 0);
+  bp_exclusive_scan_kernel<<<1, 1024, 0, t_stream>>>(pair_counts, pair_offsets, n);
+  t_launches += 5;
+  OGJK_CK(cudaGetLastError());
+  int total = 0;
+  OGJK_CK(cudaMemcpyAsync(&total, pair_offsets + n, sizeof(int), cudaMemcpyDeviceToHost, t_stream));
+  OGJK_CK(cudaStreamSynchronize(t_stream));
+  if (num_pairs) *num_pairs = total;
+  if (total > 0 && max_pairs > 0) {
+    bp_pairs_kernel<true><<<wb, 256, 0, t_stream>>>(d_pos, n, cell_size, boundary, grid_size, cell_start, cell_objs,
+                                                    nullptr, pair_offsets, d_pairs, max_pairs);
+    return finish_launch("broad phase");
+  }
+  return 0;
+}
+
 }  // namespace
 
 // =======================================================================================================
@@ -952,6 +1006,11 @@ int ogjk_stage_times(double* gjk_ms, double* epa_ms, int* calls) {
   if (calls) *calls = (int)t_stage_used;
   t_stage_used = 0;
   return 0;
+}
+int ogjk_broadphase_pairs_device(int num_objects, const float* d_pos_radius, float cell_size, float boundary,
+                                 int grid_size, void* d_pairs, int max_pairs, long long* num_pairs) {
+  return broadphase_pairs(num_objects, (const float4*)d_pos_radius, cell_size, boundary, grid_size,
+                          (CollisionPair*)d_pairs, max_pairs, num_pairs);
 }
 long long ogjk_launch_count(int reset) {
   const long long v = t_launches;

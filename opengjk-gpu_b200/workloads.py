@@ -99,7 +99,7 @@ def unit_sphere_hulls(npoly: int, nverts: int, seed: int = 2024, dtype=np.float3
 
 
 def broadphase_pool(npoly: int, nverts: int, npairs: int, seed: int = 2024, dtype=np.float32,
-                    scale_range=(0.3, 2.5)):
+                    scale_range=(0.3, 2.5), return_spheres: bool = False):
     """BASELINE config 5: a pool of `npoly` world-space hulls (unit-sphere hulls scaled by
     U[0.3,2.5], reference visualization/sim_config.h:41-44) and `npairs` candidate pairs whose
     bounding spheres overlap (what the reference's grid broad phase emits,
@@ -146,4 +146,7 @@ def broadphase_pool(npoly: int, nverts: int, npairs: int, seed: int = 2024, dtyp
     pairs = pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]
     if pairs.shape[0] > npairs:
         pairs = pairs[:npairs]
+    if return_spheres:  # (centre, bounding radius) per hull + the box edge: the input of the device broad phase
+        spheres = np.concatenate([centre, radius[:, None]], 1).astype(np.float32)
+        return pool, pairs.astype(np.int32), spheres, float(edge)
     return pool, pairs.astype(np.int32)
