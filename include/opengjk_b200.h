@@ -56,6 +56,18 @@ long long ogjk_launch_count(int reset);
  * ogjk_*_compute_minimum_distance_indexed_device / ogjk_*_compute_epa_indexed_device directly. */
 int ogjk_broadphase_pairs_device(int num_objects, const float* d_pos_radius, float cell_size, float boundary,
                                  int grid_size, void* d_pairs, int max_pairs, long long* num_pairs);
+/* Local -> world vertex transform of the polytope pool (reference visualization/integrate_final_gjk.cu:304-332
+ * transform_to_world_kernel): world = quat_rotate(quats[b], local * scales[b]) + positions[b] for every vertex of
+ * sub-mesh sm, b = sub_mesh_body[sm].  positions / quats: float4 per body (xyz + unused w / xyzw); scales: 3 floats
+ * per body; vertices: 3 floats each.  vert_offsets / vert_counts / sub_mesh_body may be NULL: then every sub-mesh has
+ * uniform_count vertices at offset sm * uniform_count and belongs to body sm.  fp32, as in the reference. */
+int ogjk_transform_to_world_device(int num_submeshes, const float* d_positions, const float* d_quats,
+                                   const float* d_scales, const float* d_verts_local, float* d_verts_world,
+                                   const int* d_vert_offsets, const int* d_vert_counts, const int* d_sub_mesh_body,
+                                   int uniform_count);
+/* Forget a pool that ogjk_*_init_polytopes_device registered for the slot-kernel fast path (call before freeing a
+ * caller-owned descriptor array; ogjk_*_free_indexed_device does it for pools the library allocated). */
+int ogjk_release_pool(const void* d_polytopes);
 /* Per-stage device timing of the fused *_gjk_epa_uniform_device calls of this thread: while enabled every call
  * records CUDA events on the launching stream before GJK, between the stages and after EPA; ogjk_stage_times waits
  * for them, returns the summed GJK / EPA milliseconds and the number of calls, and resets the list. */
@@ -149,6 +161,12 @@ int ogjk_stage_times(double* gjk_ms, double* epa_ms, int* calls);
   int ogjk_##P##_epa_uniform_device(int n, int nverts1, const OGJK_REAL* d_coord1, int nverts2,                \
                                     const OGJK_REAL* d_coord2, void* d_simplices, OGJK_REAL* d_distances,      \
                                     OGJK_REAL* d_contact_normals);                                             \
+  /* Descriptor upkeep of a device-resident pool (reference visualization/integrate_final_gjk.cu:691-704             \
+   * init_polytopes_kernel): polytopes[sm] = {numpoints = vert_counts[sm], coord = verts_world + 3*vert_offsets[sm],  \
+   * s = 0, s_idx = 0}.  With NULL offsets/counts the pool is uniform (uniform_count vertices each, dense) and, when   \
+   * uniform_count % 4 == 0, indexed batches over it take the slot kernels. */                                         \
+  int ogjk_##P##_init_polytopes_device(void* d_polytopes, OGJK_REAL* d_verts_world, const int* d_vert_offsets,        \
+                                       const int* d_vert_counts, int uniform_count, int num_submeshes);                \
   /* GJK followed by EPA in one call (what compute_gjk_epa does after its upload, reference                   \
    * GJK/gpu/openGJK.cu:2854-2883); lets the library fuse the EPA gate into the GJK kernel. */                 \
   int ogjk_##P##_gjk_epa_uniform_device(int n, int nverts1, const OGJK_REAL* d_coord1, int nverts2,            \

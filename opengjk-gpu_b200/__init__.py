@@ -155,6 +155,21 @@ class Engine:
             raise OgjkError(f"ogjk_broadphase_pairs_device failed ({rc}): {self.lib.ogjk_last_error().decode()}")
         return int(total.value)
 
+    def transform_to_world_device(self, n_sub, d_positions, d_quats, d_scales, d_local, d_world, d_offsets=None,
+                                  d_counts=None, d_sub_body=None, uniform_count=0):
+        rc = self.lib.ogjk_transform_to_world_device(ctypes.c_int(n_sub), _ptr(d_positions), _ptr(d_quats), _ptr(d_scales),
+                                                     _ptr(d_local), _ptr(d_world), _ptr(d_offsets), _ptr(d_counts),
+                                                     _ptr(d_sub_body), ctypes.c_int(uniform_count))
+        if rc != 0:
+            raise OgjkError(f"ogjk_transform_to_world_device failed ({rc}): {self.lib.ogjk_last_error().decode()}")
+
+    def init_polytopes_device(self, d_polytopes, d_world, n_sub, d_offsets=None, d_counts=None, uniform_count=0):
+        self._call("init_polytopes_device", _ptr(d_polytopes), _ptr(d_world), _ptr(d_offsets), _ptr(d_counts),
+                   ctypes.c_int(uniform_count), ctypes.c_int(n_sub))
+
+    def release_pool(self, d_polytopes):
+        self.lib.ogjk_release_pool(_ptr(d_polytopes))
+
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.ogjk_launch_count(ctypes.c_int(int(reset))))
 

@@ -18,6 +18,7 @@
 #include "epa_kernel.cuh"
 #include "epa_group.cuh"
 #include "broadphase.cuh"
+#include "transform.cuh"
 #include "gjk_generic.cuh"
 #include "gjk_tables.h"
 #include "gjk_slots.cuh"
@@ -1007,6 +1008,22 @@ int ogjk_stage_times(double* gjk_ms, double* epa_ms, int* calls) {
   t_stage_used = 0;
   return 0;
 }
+int ogjk_transform_to_world_device(int num_submeshes, const float* d_positions, const float* d_quats,
+                                   const float* d_scales, const float* d_verts_local, float* d_verts_world,
+                                   const int* d_vert_offsets, const int* d_vert_counts, const int* d_sub_mesh_body,
+                                   int uniform_count) {
+  if (num_submeshes <= 0) return 0;
+  if (!d_positions || !d_quats || !d_scales || !d_verts_local || !d_verts_world) return fail_msg("null argument");
+  if ((!d_vert_offsets || !d_vert_counts) && uniform_count < 1) return fail_msg("vertex layout missing");
+  transform_to_world_kernel<<<(unsigned)num_submeshes, 64, 0, t_stream>>>(
+      (const float4*)d_positions, (const float4*)d_quats, d_scales, d_verts_local, d_verts_world, d_vert_offsets,
+      d_vert_counts, d_sub_mesh_body, uniform_count, num_submeshes);
+  return finish_launch("transform_to_world");
+}
+int ogjk_release_pool(const void* d_polytopes) {
+  unregister_pool(d_polytopes);
+  return 0;
+}
 int ogjk_broadphase_pairs_device(int num_objects, const float* d_pos_radius, float cell_size, float boundary,
                                  int grid_size, void* d_pairs, int max_pairs, long long* num_pairs) {
   return broadphase_pairs(num_objects, (const float4*)d_pos_radius, cell_size, boundary, grid_size,
@@ -1194,6 +1211,20 @@ long long ogjk_launch_count(int reset) {
     return run_indexed_host<REAL>(num_polytopes, num_pairs, (const PolytopeT<REAL>*)polytopes,                         \
                                   (const CollisionPair*)pairs, (SimplexT<REAL>*)simplices, distances,                  \
                                   contact_normals, kGjk | kEpa);                                                       \
+  }                                                                                                                    \
+  int ogjk_##P##_init_polytopes_device(void* d_polytopes, REAL* d_verts_world, const int* d_vert_offsets,             \
+                                       const int* d_vert_counts, int uniform_count, int num_submeshes) {              \
+    if (num_submeshes <= 0) return 0;                                                                                  \
+    if (!d_polytopes || !d_verts_world) return fail_msg("null argument");                                              \
+    const bool uniform = !d_vert_offsets || !d_vert_counts;                                                            \
+    if (uniform && uniform_count < 1) return fail_msg("vertex layout missing");                                        \
+    init_polytopes_kernel<REAL><<<(unsigned)((num_submeshes + 255) / 256), 256, 0, t_stream>>>(                        \
+        (PolytopeT<REAL>*)d_polytopes, d_verts_world, uniform ? nullptr : d_vert_offsets,                              \
+        uniform ? nullptr : d_vert_counts, uniform_count, num_submeshes);                                              \
+    unregister_pool(d_polytopes);                                                                                      \
+    if (uniform && uniform_count % 4 == 0 && ((uintptr_t)d_verts_world & 15u) == 0)                                    \
+      register_pool(d_polytopes, d_verts_world, uniform_count, num_submeshes);                                         \
+    return finish_launch("init_polytopes");                                                                            \
   }                                                                                                                    \
   int ogjk_##P##_gjk_uniform_device(int n, int nverts1, const REAL* d_coord1, int nverts2, const REAL* d_coord2,      \
                                     void* d_simplices, REAL* d_distances) {                                           \
