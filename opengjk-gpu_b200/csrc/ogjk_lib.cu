@@ -461,14 +461,15 @@ int launch_gjk_epa_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, Si
 constexpr int kGjkStage = 1, kEpaStage = 2;  // = Stage::kGjk, Stage::kEpa below
 struct PoolInfo {
   const void* coords;
-  int nv;
+  int nv;      // > 0: uniform pool, dense coordinates; 0: only `max_nv` is known
   int count;
+  int max_nv;  // vertex-count hint for the general kernel's lane selection
 };
 std::mutex g_pool_mutex;
 std::vector<std::pair<const void*, PoolInfo>> g_pools;  // keyed by the device descriptor pointer
-void register_pool(const void* d_desc, const void* d_coords, int nv, int count) {
+void register_pool(const void* d_desc, const void* d_coords, int nv, int count, int max_nv = 0) {
   std::lock_guard<std::mutex> lock(g_pool_mutex);
-  g_pools.push_back({d_desc, PoolInfo{d_coords, nv, count}});
+  g_pools.push_back({d_desc, PoolInfo{d_coords, nv, count, max_nv > 0 ? max_nv : nv}});
 }
 void unregister_pool(const void* d_desc) {
   std::lock_guard<std::mutex> lock(g_pool_mutex);
@@ -561,6 +562,9 @@ struct Flattened {
 };
 
 template <typename T>
+bool dense_uniform_range(const PolytopeT<T>* bd, size_t lo, size_t hi);  // below
+
+template <typename T>
 int flatten_upload(int n, const PolytopeT<T>* bd, Flattened<T>& out) {
   size_t total = 0;
   long long max_nv = 0;
@@ -573,6 +577,32 @@ int flatten_upload(int n, const PolytopeT<T>* bd, Flattened<T>& out) {
     if (bd[i].numpoints != bd[0].numpoints) uniform = false;
   }
   out.uniform_nv = uniform ? bd[0].numpoints : 0;
+  out.max_nv = max_nv;
+  if (uniform && dense_uniform_range(bd, 0, (size_t)n)) {
+    // Uniform batch whose coordinates already lie back to back in the caller's memory (what every driver of the
+    // reference builds): no staging copy -- one DMA straight from the caller's array -- and the descriptors are
+    // written on the device instead of being staged and uploaded (the reference stages both, openGJK.cu:2917-2948).
+    cudaError_t e;
+    if ((e = cudaMalloc(&out.d_coord, total * sizeof(T))) != cudaSuccess) return fail("cudaMalloc(coords)", e);
+    if ((e = cudaMalloc(&out.d_desc, (size_t)n * sizeof(PolytopeT<T>))) != cudaSuccess) {
+      cudaFree(out.d_coord);
+      out.d_coord = nullptr;
+      return fail("cudaMalloc(desc)", e);
+    }
+    init_polytopes_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, t_stream>>>(out.d_desc, out.d_coord, nullptr, nullptr,
+                                                                            bd[0].numpoints, n);
+    ++t_launches;
+    e = cudaMemcpyAsync(out.d_coord, bd[0].coord, total * sizeof(T), cudaMemcpyHostToDevice, t_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(t_stream);
+    if (e != cudaSuccess) {
+      cudaFree(out.d_coord);
+      cudaFree(out.d_desc);
+      out.d_coord = nullptr;
+      out.d_desc = nullptr;
+      return fail("H2D coords", e);
+    }
+    return 0;
+  }
   T* h_coord = nullptr;
   PolytopeT<T>* h_desc = nullptr;
   OGJK_CK(cudaMallocHost(&h_coord, total * sizeof(T)));
@@ -886,7 +916,7 @@ int run_indexed_host(int num_polytopes, int num_pairs, const PolytopeT<T>* polyt
     {
       SyncOverride nosync;
       IndexedSource<T> src{pool.d_desc, d_pairs};
-      const PoolInfo info{pool.d_coord, pool.uniform_nv, num_polytopes};
+      const PoolInfo info{pool.d_coord, pool.uniform_nv, num_polytopes, (int)pool.max_nv};
       rc = launch_indexed_uniform<T>(num_pairs, info, d_pairs, pool.d_desc, d_simp, d_dist, d_nrm, stages);
       if (rc < 0 || (rc != 0 && rc != 1)) break;
       if (rc == 1) {  // not a uniform fp32 pool / small batch: the general kernels
@@ -1072,6 +1102,9 @@ long long ogjk_launch_count(int reset) {
     *d_bd2 = f2.d_desc;                                                                                                \
     *d_coord1 = f1.d_coord;                                                                                            \
     *d_coord2 = f2.d_coord;                                                                                            \
+    /* remembered so that the *_device calls on these arrays can take the dense fast kernels (and skip the peek) */   \
+    register_pool(f1.d_desc, f1.d_coord, f1.uniform_nv, n, (int)f1.max_nv);                                            \
+    register_pool(f2.d_desc, f2.d_coord, f2.uniform_nv, n, (int)f2.max_nv);                                            \
     OGJK_CK(cudaMalloc(d_simplices, (size_t)n * sizeof(SimplexT<REAL>)));                                              \
     OGJK_CK(cudaMalloc((void**)d_distances, (size_t)n * sizeof(REAL)));                                                \
     OGJK_CK(cudaMemsetAsync(*d_simplices, 0, (size_t)n * sizeof(SimplexT<REAL>), t_stream));                           \
@@ -1082,7 +1115,15 @@ long long ogjk_launch_count(int reset) {
                                                  REAL* d_distances) {                                                 \
     if (n <= 0) return 0;                                                                                              \
     int nv = 0;                                                                                                        \
-    if (int rc = peek_numpoints<REAL>((const PolytopeT<REAL>*)d_bd1, &nv)) return rc;                                  \
+    PoolInfo p1, p2;                                                                                                   \
+    const bool known = lookup_pool(d_bd1, &p1) && lookup_pool(d_bd2, &p2) && p1.count >= n && p2.count >= n;           \
+    if (known && p1.nv > 0 && p2.nv > 0) { /* arrays uploaded by allocate_and_copy_device_arrays, uniform + dense */   \
+      const int fast = launch_gjk_uniform<REAL>(n, p1.nv, (const REAL*)p1.coords, p2.nv, (const REAL*)p2.coords,       \
+                                                (SimplexT<REAL>*)d_simplices, d_distances);                            \
+      if (fast <= 0) return fast;                                                                                      \
+    }                                                                                                                  \
+    if (known) nv = p1.max_nv;                                                                                         \
+    else if (int rc = peek_numpoints<REAL>((const PolytopeT<REAL>*)d_bd1, &nv)) return rc;                             \
     DescSource<REAL> src{(const PolytopeT<REAL>*)d_bd1, (const PolytopeT<REAL>*)d_bd2};                                \
     return launch_gjk_generic<REAL>(src, n, nv, (SimplexT<REAL>*)d_simplices, d_distances);                            \
   }                                                                                                                    \
@@ -1103,6 +1144,8 @@ long long ogjk_launch_count(int reset) {
   }                                                                                                                    \
   int ogjk_##P##_free_device_arrays(void* d_bd1, void* d_bd2, REAL* d_coord1, REAL* d_coord2, void* d_simplices,      \
                                     REAL* d_distances) {                                                              \
+    unregister_pool(d_bd1);                                                                                            \
+    unregister_pool(d_bd2);                                                                                            \
     cudaFree(d_bd1);                                                                                                   \
     cudaFree(d_bd2);                                                                                                   \
     cudaFree(d_coord1);                                                                                                \
