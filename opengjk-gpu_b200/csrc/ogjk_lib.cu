@@ -119,6 +119,36 @@ int finish_launch(const char* what) {
   return 0;
 }
 
+// Launch configuration of the persistent kernels, memoised per (thread, device, kernel, shared-memory size): the
+// dynamic shared-memory opt-in and the occupancy query cost ~10 us of host time per call, which a small batch would
+// see as GPU idle time in front of every launch.
+struct LaunchCfg {
+  int dev;
+  const void* fn;
+  size_t smem;
+  int grid_per_device;  // SMs x resident CTAs per SM
+};
+thread_local std::vector<LaunchCfg> t_cfgs;
+template <typename Kernel>
+int persistent_grid(Kernel kern, int threads, size_t smem, long long* grid) {
+  int dev = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  const void* fn = reinterpret_cast<const void*>(kern);
+  for (const LaunchCfg& c : t_cfgs)
+    if (c.dev == dev && c.fn == fn && c.smem == smem) {
+      *grid = c.grid_per_device;
+      return 0;
+    }
+  int sms = 0, per_sm = 0;
+  if (smem > 48u * 1024u) OGJK_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) return fail_msg("persistent kernel does not fit on this device");
+  t_cfgs.push_back(LaunchCfg{dev, fn, smem, sms * per_sm});
+  *grid = (long long)sms * per_sm;
+  return 0;
+}
+
 // lanes per pair for the general kernel, from a typical vertex count
 int lanes_for(int nv) {
   if (nv <= 16) return 4;
@@ -173,7 +203,7 @@ unsigned slots_prefetch_ahead() {
 
 int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist,
                      const CollisionPair* pairs = nullptr) {
-  int dev = 0, sms = 0, per_sm = 0;
+  int dev = 0;
   OGJK_CK(cudaGetDevice(&dev));
   const uint16_t* utab = nullptr;
   if (int rc = device_unified_table(&utab)) return rc;
@@ -181,11 +211,8 @@ int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, 
   const size_t smem = (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2);
   // the interleaved scan needs ~40 more registers: only where shared memory, not registers, bounds occupancy
   auto kern = (nv1 == nv2 && nv1 >= 32) ? gjk_slots_kernel<true> : gjk_slots_kernel<false>;
-  OGJK_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSlotThreads, smem));
-  if (per_sm < 1) return fail_msg("slot kernel does not fit on this device");
-  long long grid = (long long)sms * per_sm;
+  long long grid = 0;
+  if (int rc = persistent_grid(kern, kSlotThreads, smem, &grid)) return rc;
   const long long need = ((long long)n + kSlotThreads - 1) / kSlotThreads;
   if (grid > need) grid = need;
   OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
@@ -227,7 +254,7 @@ int ws_compute_warps(int nv1, int nv2) {
 template <int CW, int LP>
 int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp,
                            float* dist, float* nrm, int* queue, int* count, const CollisionPair* pairs) {
-  int dev = 0, sms = 0, per_sm = 0;
+  int dev = 0;
   OGJK_CK(cudaGetDevice(&dev));
   const uint16_t* utab = nullptr;
   if (int rc = device_unified_table(&utab)) return rc;
@@ -238,11 +265,8 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float
   auto kern = pairs ? gjk_slots_ws_kernel<CW, LP, LP == 1, true>  // one pool: equal vertex counts by construction
                     : (LP == 1 && nv1 == nv2) ? gjk_slots_ws_kernel<CW, LP, true, false>
                                               : gjk_slots_ws_kernel<CW, LP, false, false>;
-  OGJK_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-  if (per_sm < 1) return fail_msg("slot kernel does not fit on this device");
-  long long grid = (long long)sms * per_sm;
+  long long grid = 0;
+  if (int rc = persistent_grid(kern, threads, smem, &grid)) return rc;
   const long long need = ((long long)n + nslots - 1) / nslots;
   if (grid > need) grid = need;
   OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
