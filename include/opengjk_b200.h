@@ -167,6 +167,22 @@ int ogjk_stage_times(double* gjk_ms, double* epa_ms, int* calls);
    * uniform_count % 4 == 0, indexed batches over it take the slot kernels. */                                         \
   int ogjk_##P##_init_polytopes_device(void* d_polytopes, OGJK_REAL* d_verts_world, const int* d_vert_offsets,        \
                                        const int* d_vert_counts, int uniform_count, int num_submeshes);                \
+  /* Contact response over the hot path's outputs (reference visualization/integrate_final_gjk.cu:572-689              \
+   * collision_response_kernel and its call site :1039-1054): for every pair with distance <= params[0] the Baumgarte  \
+   * position correction (distance < 0) and the normal impulse on linear / angular velocity, bodies = sub_mesh_body of  \
+   * the pair's two indices (NULL: the indices themselves).  positions / vel / ang / quats: float4 per body (vel.w =    \
+   * mass as in the reference), inv_inertia: 3 floats per body.  d_vel_pong / d_ang_pong receive ping + impulses for     \
+   * EVERY body (the reference's ping -> pong cudaMemcpy is folded in); d_positions is corrected in place.              \
+   * params = {epsilon, restitution, restitution_threshold, baumgarte_beta} (reference sim_config.h:60-64: 0.7, 2.0,    \
+   * 0.2).  Deterministic: a body's contributions are added in ascending pair order, all pairs read the positions as    \
+   * they were on entry (the reference's atomicAdd order is whatever the hardware makes it).  Physics state is fp32    \
+   * in both precisions, as in the reference. */                                                                        \
+  int ogjk_##P##_contact_response_device(int num_pairs, const void* d_pairs, const OGJK_REAL* d_distances,             \
+                                         const void* d_simplices, const OGJK_REAL* d_contact_normals,                  \
+                                         const int* d_sub_mesh_body, int num_objects, float* d_positions,              \
+                                         const float* d_vel_ping, float* d_vel_pong, const float* d_ang_ping,          \
+                                         float* d_ang_pong, const float* d_quats, const float* d_inv_inertia,          \
+                                         const float* params);                                                         \
   /* GJK followed by EPA in one call (what compute_gjk_epa does after its upload, reference                   \
    * GJK/gpu/openGJK.cu:2854-2883); lets the library fuse the EPA gate into the GJK kernel. */                 \
   int ogjk_##P##_gjk_epa_uniform_device(int n, int nverts1, const OGJK_REAL* d_coord1, int nverts2,            \

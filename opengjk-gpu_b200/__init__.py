@@ -167,6 +167,17 @@ class Engine:
         self._call("init_polytopes_device", _ptr(d_polytopes), _ptr(d_world), _ptr(d_offsets), _ptr(d_counts),
                    ctypes.c_int(uniform_count), ctypes.c_int(n_sub))
 
+    def contact_response_device(self, num_pairs, d_pairs, d_distances, d_simplices, d_normals, num_objects, d_positions,
+                                d_vel_ping, d_vel_pong, d_ang_ping, d_ang_pong, d_quats, d_inv_inertia,
+                                d_sub_mesh_body=None, epsilon=0.0, restitution=0.7, restitution_threshold=2.0,
+                                baumgarte_beta=0.2):
+        """contact response over GJK/EPA outputs (reference collision_response_kernel); corrects d_positions in place
+        and writes ping + impulses to the pong buffers; defaults = reference visualization/sim_config.h:60-64"""
+        prm = (ctypes.c_float * 4)(epsilon, restitution, restitution_threshold, baumgarte_beta)
+        self._call("contact_response_device", ctypes.c_int(num_pairs), _ptr(d_pairs), _ptr(d_distances), _ptr(d_simplices),
+                   _ptr(d_normals), _ptr(d_sub_mesh_body), ctypes.c_int(num_objects), _ptr(d_positions), _ptr(d_vel_ping),
+                   _ptr(d_vel_pong), _ptr(d_ang_ping), _ptr(d_ang_pong), _ptr(d_quats), _ptr(d_inv_inertia), prm)
+
     def release_pool(self, d_polytopes):
         self.lib.ogjk_release_pool(_ptr(d_polytopes))
 

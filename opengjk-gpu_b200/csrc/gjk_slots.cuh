@@ -320,46 +320,112 @@ struct TicketFeed {
   }
 };
 
+// ---- fp64 slots ----------------------------------------------------------------------------------------------------
+// A block of four vertices is 96 bytes = six 16-byte chunks; there is no packed fp64 multiply, so the scan is scalar
+// DMUL/DADD.  Same structure as the fp32 scan: one block ahead, (max, block) tracking, exact recovery.
+struct Block4d {
+  double2 a, b, c, d, e, f;  // x0 y0 | z0 x1 | y1 z1 | x2 y2 | z2 x3 | y3 z3
+};
+OGJK_D Block4d load_block(const double2* chunk, int g) {
+  Block4d k;
+  k.a = chunk[6 * g];
+  k.b = chunk[6 * g + 1];
+  k.c = chunk[6 * g + 2];
+  k.d = chunk[6 * g + 3];
+  k.e = chunk[6 * g + 4];
+  k.f = chunk[6 * g + 5];
+  return k;
+}
+OGJK_D void dots4(const Block4d& k, const V3<double>& D, double (&dd)[4]) {
+  dd[0] = add_rn(add_rn(mul_rn(k.a.x, D.x), mul_rn(k.a.y, D.y)), mul_rn(k.b.x, D.z));
+  dd[1] = add_rn(add_rn(mul_rn(k.b.y, D.x), mul_rn(k.c.x, D.y)), mul_rn(k.c.y, D.z));
+  dd[2] = add_rn(add_rn(mul_rn(k.d.x, D.x), mul_rn(k.d.y, D.y)), mul_rn(k.e.x, D.z));
+  dd[3] = add_rn(add_rn(mul_rn(k.e.y, D.x), mul_rn(k.f.x, D.y)), mul_rn(k.f.y, D.z));
+}
+OGJK_D double max4(const double (&dd)[4]) { return fmax(fmax(dd[0], dd[1]), fmax(dd[2], dd[3])); }
+OGJK_D void support_slot(const double* body, int nv, const V3<double>& d, unsigned, V3<double>& sup, int& sup_idx) {
+  const double2* chunk = reinterpret_cast<const double2*>(body);
+  double best = -INFINITY;
+  int bg = 0;
+  const int groups = nv >> 2;
+  Block4d k0 = load_block(chunk, 0);
+#pragma unroll 2
+  for (int g = 0; g < groups; ++g) {
+    const Block4d n0 = load_block(chunk, g + 1);  // look-ahead; past the end it is discarded
+    double da[4];
+    dots4(k0, d, da);
+    const double ma = max4(da);
+    if (ma > best) {  // strict: the earliest block holding the maximum wins
+      best = ma;
+      bg = g;
+    }
+    k0 = n0;
+  }
+  if (best > dot(sup, d)) {
+    double dd[4];
+    dots4(load_block(chunk, bg), d, dd);
+    int k = 3;
+    if (dd[2] == best) k = 2;
+    if (dd[1] == best) k = 1;
+    if (dd[0] == best) k = 0;
+    const int idx = 4 * bg + k;
+    sup = mk<double>(body[3 * idx], body[3 * idx + 1], body[3 * idx + 2]);
+    sup_idx = idx;
+  }
+}
+OGJK_D void support_slots_both(const double* b1, const double* b2, int nv, const V3<double>& v, unsigned zero,
+                               V3<double>& sup1, int& idx1, V3<double>& sup2, int& idx2) {
+  support_slot(b1, nv, vneg(v), zero, sup1, idx1);
+  support_slot(b2, nv, v, zero, sup2, idx2);
+}
+
+// integers travel through the finisher's records as bit patterns of T
+OGJK_D float rec_from_int(float, unsigned v) { return __uint_as_float(v); }
+OGJK_D double rec_from_int(double, unsigned v) { return __longlong_as_double((long long)v); }
+OGJK_D unsigned rec_to_uint(float x) { return __float_as_uint(x); }
+OGJK_D unsigned rec_to_uint(double x) { return (unsigned)__double_as_longlong(x); }
+
+template <typename T>
 struct SlotFetch {
-  const float* b1;
-  const float* b2;
-  OGJK_D V3<float> operator()(int body, int i) const {
-    const float* c = body ? b2 : b1;
-    return mk<float>(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
+  const T* b1;
+  const T* b2;
+  OGJK_D V3<T> operator()(int body, int i) const {
+    const T* c = body ? b2 : b1;
+    return mk<T>(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
   }
 };
 
 constexpr int kSlotThreads = 128;
 constexpr uint32_t kSlotTableBytes = (kUnifiedSize * 2u + 15u) & ~15u;
 constexpr uint32_t kSlotFixedBytes = kSlotThreads * 8u + kSlotTableBytes;  // mbarriers + table
-constexpr uint32_t kSlotPadBytes = 96;  // look-ahead loads of the last slot stay inside the allocation
+constexpr uint32_t kSlotPadBytes = 192;  // look-ahead loads of the last slot stay inside the allocation
 
 // bytes of one slot: both vertex sets, rounded so that (bytes / 16) is odd
-__host__ __device__ inline uint32_t slot_bytes(int nv1, int nv2) {
-  uint32_t units = (uint32_t)(nv1 + nv2) * 12u / 16u;
+__host__ __device__ inline uint32_t slot_bytes(int nv1, int nv2, int esize = 4) {
+  uint32_t units = (uint32_t)(nv1 + nv2) * 3u * (uint32_t)esize / 16u;
   if ((units & 1u) == 0) units += 1;
   return units * 16u;
 }
 
 // EQ: both bodies have the same vertex count (selects the interleaved two-body scan; the other scan is not even
 // instantiated then, which keeps the loop body small for the instruction cache)
-template <bool EQ>
+template <typename T, bool EQ>
 __global__ void __launch_bounds__(kSlotThreads)
-gjk_slots_kernel(const float* __restrict__ coord1, const float* __restrict__ coord2, int nv1, int nv2,
-                 SimplexT<float>* __restrict__ simplices, float* __restrict__ distances, unsigned n,
+gjk_slots_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, int nv1, int nv2,
+                 SimplexT<T>* __restrict__ simplices, T* __restrict__ distances, unsigned n,
                  const uint16_t* __restrict__ utab_g, unsigned* __restrict__ ticket, unsigned prefetch_ahead,
                  unsigned zero, const CollisionPair* __restrict__ pairs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t sbytes = slot_bytes(nv1, nv2);
+  const uint32_t sbytes = slot_bytes(nv1, nv2, (int)sizeof(T));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // one mbarrier per thread
   uint16_t* utab = reinterpret_cast<uint16_t*>(smem_raw + kSlotThreads * 8u);
   unsigned char* slots = smem_raw + kSlotFixedBytes;
   const int tid = threadIdx.x, lane = tid & 31;
-  const float* s1 = reinterpret_cast<const float*>(slots + (size_t)tid * sbytes);
-  const float* s2 = s1 + 3 * nv1;
+  const T* s1 = reinterpret_cast<const T*>(slots + (size_t)tid * sbytes);
+  const T* s2 = s1 + 3 * nv1;
   const uint32_t bar = smem_addr(&bars[tid]);
   const uint32_t dst1 = smem_addr(s1), dst2 = smem_addr(s2);
-  const uint32_t bytes1 = (uint32_t)nv1 * 12u, bytes2 = (uint32_t)nv2 * 12u;
+  const uint32_t bytes1 = (uint32_t)nv1 * 3u * (uint32_t)sizeof(T), bytes2 = (uint32_t)nv2 * 3u * (uint32_t)sizeof(T);
 
   for (int i = tid; i < kUnifiedSize / 2; i += kSlotThreads)
     reinterpret_cast<uint32_t*>(utab)[i] = __ldg(reinterpret_cast<const uint32_t*>(utab_g) + i);
@@ -374,7 +440,7 @@ gjk_slots_kernel(const float* __restrict__ coord1, const float* __restrict__ coo
   unsigned pair = 0;
   TicketFeed feed;
   feed.init(ticket, pairs, n, lane);
-  GjkState<float> g;
+  GjkState<T> g;
   (void)prefetch_ahead;
 
   for (;;) {
@@ -400,7 +466,7 @@ gjk_slots_kernel(const float* __restrict__ coord1, const float* __restrict__ coo
 
     if (state == kLoading && mbar_test_wait(bar, parity)) {
       parity ^= 1u;
-      gjk_init(g, mk<float>(s1[0], s1[1], s1[2]), mk<float>(s2[0], s2[1], s2[2]));
+      gjk_init(g, mk<T>(s1[0], s1[1], s1[2]), mk<T>(s2[0], s2[1], s2[2]));
       state = kRunning;
     }
     if (state == kRunning) {
@@ -412,8 +478,8 @@ gjk_slots_kernel(const float* __restrict__ coord1, const float* __restrict__ coo
         support_slot(s2, nv2, g.v, zero, g.sup2, g.idx2);
       }
       if (gjk_advance_u(g, utab)) {
-        SlotFetch fetch{s1, s2};
-        V3<float> w1, w2;
+        SlotFetch<T> fetch{s1, s2};
+        V3<T> w1, w2;
         gjk_witnesses(fetch, g.S, w1, w2);
         store_result(simplices + pair, distances + pair, g, w1, w2);
         state = kNeedWork;
@@ -429,15 +495,16 @@ gjk_slots_kernel(const float* __restrict__ coord1, const float* __restrict__ coo
 struct SlotLayout {
   uint32_t stride, body2;  // bytes
 };
-__host__ __device__ inline SlotLayout ws_slot_layout(int nv1, int nv2, int lp) {
+__host__ __device__ inline SlotLayout ws_slot_layout(int nv1, int nv2, int lp, int esize = 4) {
   SlotLayout L;
+  const uint32_t vb = 3u * (uint32_t)esize;  // bytes per vertex
   if (lp == 1) {
-    L.stride = slot_bytes(nv1, nv2);
-    L.body2 = (uint32_t)nv1 * 12u;
+    L.stride = slot_bytes(nv1, nv2, esize);
+    L.body2 = (uint32_t)nv1 * vb;
   } else {
-    uint32_t u1 = ((uint32_t)nv1 * 12u + 15u) / 16u;
+    uint32_t u1 = ((uint32_t)nv1 * vb + 15u) / 16u;
     if ((u1 & 1u) == 0) u1 += 1;
-    uint32_t u = u1 + ((uint32_t)nv2 * 12u + 15u) / 16u;
+    uint32_t u = u1 + ((uint32_t)nv2 * vb + 15u) / 16u;
     while ((u & 3u) != 2u) ++u;
     L.stride = u * 16u;
     L.body2 = u1 * 16u;
@@ -463,25 +530,27 @@ __host__ __device__ inline SlotLayout ws_slot_layout(int nv1, int nv2, int lp) {
 // Synchronisation: slot flag FREE/BUSY/EXIT (plain shared words, fences), per-slot mbarrier for TMA completion (the
 // loader's arrive.expect_tx releases its `pair_of` store to the waiting compute thread), ring with a reservation
 // counter (shared atomic), per-record generation flags and a consumer-published head.
-constexpr int kRingRecords = 64;
+// ring capacity: 64 records, 32 when the CTA has only 64 slots (keeps 64+64-vertex fp64 slots within shared memory)
+__host__ __device__ constexpr int ring_records(int nslots) { return nslots >= 128 ? 64 : 32; }
 constexpr int kRecWords = 49;  // odd stride: lanes writing/reading consecutive records hit distinct banks
 // record layout (words): 0 pair | 1 n | 2..4 v | 5+5k.. slot k: p.xyz, i1, i2 | 25+6k.. slot k: body-1 xyz, body-2 xyz
 enum : unsigned { kSlotFree = 0u, kSlotBusy = 1u, kSlotExit = 2u };
 
-__host__ __device__ constexpr uint32_t ws_fixed_bytes(int nslots) {
-  // mbarriers | table | ctrl | pair_of | ring control (16 B) | ready flags | ring
-  return (uint32_t)nslots * 8u + kSlotTableBytes + (uint32_t)nslots * 4u * 2u + 16u + kRingRecords * 4u +
-         ((kRingRecords * kRecWords * 4u + 15u) & ~15u);
+__host__ __device__ constexpr uint32_t ws_fixed_bytes(int nslots, int esize = 4) {
+  // mbarriers | table | ctrl | pair_of | ring control (16 B) | ready flags | ring (kRecWords elements of T per record)
+  return (uint32_t)nslots * 8u + kSlotTableBytes + (uint32_t)nslots * 4u * 2u + 16u + ring_records(nslots) * 4u +
+         (((uint32_t)ring_records(nslots) * kRecWords * (uint32_t)esize + 15u) & ~15u);
 }
 
 OGJK_D unsigned ld_vol(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
 OGJK_D void st_vol(unsigned* p, unsigned v) { *reinterpret_cast<volatile unsigned*>(p) = v; }
 
+template <typename T>
 struct RecordFetch {  // vertex "index" = original simplex slot in bits 30..31 (see the finisher)
-  const float* verts;  // record words 25..48
-  OGJK_D V3<float> operator()(int body, int i) const {
-    const float* c = verts + 6 * ((unsigned)i >> 30) + 3 * body;
-    return mk<float>(c[0], c[1], c[2]);
+  const T* verts;  // record words 25..48
+  OGJK_D V3<T> operator()(int body, int i) const {
+    const T* c = verts + 6 * ((unsigned)i >> 30) + 3 * body;
+    return mk<T>(c[0], c[1], c[2]);
   }
 };
 
@@ -491,17 +560,18 @@ struct RecordFetch {  // vertex "index" = original simplex slot in bits 30..31 (
 // issue from while the first waits on a dependency.
 // IDX: pairs are gkCollisionPair records into one pool (ticket feed with record prefetch); otherwise pair t is
 // (coord1[t], coord2[t]) and the loader draws plain ticket ranges.
-template <int CW, int LP, bool EQ, bool IDX>
+template <typename T, int CW, int LP, bool EQ, bool IDX>
 __global__ void __launch_bounds__((CW + 2) * 32)
-gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ coord2, int nv1, int nv2,
-                    SimplexT<float>* __restrict__ simplices, float* __restrict__ distances, unsigned n,
+gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, int nv1, int nv2,
+                    SimplexT<T>* __restrict__ simplices, T* __restrict__ distances, unsigned n,
                     const uint16_t* __restrict__ utab_g, unsigned* __restrict__ ticket, unsigned zero,
-                    float* __restrict__ normals, int* __restrict__ epa_queue, int* __restrict__ epa_count,
+                    T* __restrict__ normals, int* __restrict__ epa_queue, int* __restrict__ epa_count,
                     const CollisionPair* __restrict__ pairs, unsigned dense_chunk) {
   constexpr int kCompute = CW * 32;
   constexpr int kSlots = kCompute / LP;
+  constexpr int kRingRecords = ring_records(kSlots);
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const SlotLayout lay = ws_slot_layout(nv1, nv2, LP);
+  const SlotLayout lay = ws_slot_layout(nv1, nv2, LP, (int)sizeof(T));
   const uint32_t sbytes = lay.stride;
   unsigned char* sp = smem_raw;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sp);
@@ -516,10 +586,10 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
   sp += 16;
   unsigned* ready = reinterpret_cast<unsigned*>(sp);
   sp += kRingRecords * 4;
-  float* ring = reinterpret_cast<float*>(sp);
-  unsigned char* slots = smem_raw + ws_fixed_bytes(kSlots);
+  T* ring = reinterpret_cast<T*>(sp);
+  unsigned char* slots = smem_raw + ws_fixed_bytes(kSlots, (int)sizeof(T));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t bytes1 = (uint32_t)nv1 * 12u, bytes2 = (uint32_t)nv2 * 12u;
+  const uint32_t bytes1 = (uint32_t)nv1 * 3u * (uint32_t)sizeof(T), bytes2 = (uint32_t)nv2 * 3u * (uint32_t)sizeof(T);
 
   for (int i = tid; i < kUnifiedSize / 2; i += (CW + 2) * 32)
     reinterpret_cast<uint32_t*>(utab)[i] = __ldg(reinterpret_cast<const uint32_t*>(utab_g) + i);
@@ -537,20 +607,20 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
   if (warp < CW) {
     // ================================================ compute ================================================
     const int cslot = tid / LP, half = tid % LP;
-    const float* s1 = reinterpret_cast<const float*>(slots + (size_t)cslot * sbytes);
-    const float* s2 = reinterpret_cast<const float*>(slots + (size_t)cslot * sbytes + lay.body2);
+    const T* s1 = reinterpret_cast<const T*>(slots + (size_t)cslot * sbytes);
+    const T* s2 = reinterpret_cast<const T*>(slots + (size_t)cslot * sbytes + lay.body2);
     const uint32_t bar = smem_addr(&bars[cslot]);
     enum { kWait = 0, kRun = 1, kExit = 2 };
     int state = kWait;
     uint32_t parity = 0;
     unsigned pair = 0;
-    GjkState<float> g;
+    GjkState<T> g;
     for (;;) {
       if (state == kWait) {
         if (mbar_test_wait(bar, parity)) {
           parity ^= 1u;
           pair = ld_vol(&pair_of[cslot]);
-          gjk_init(g, mk<float>(s1[0], s1[1], s1[2]), mk<float>(s2[0], s2[1], s2[2]));
+          gjk_init(g, mk<T>(s1[0], s1[1], s1[2]), mk<T>(s2[0], s2[1], s2[2]));
           state = kRun;
         } else if (ld_vol(&ctrl[cslot]) == kSlotExit) {
           state = kExit;
@@ -578,16 +648,16 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
           }
         } else {
           // this lane's body: half 0 scans body 1 along -v, half 1 scans body 2 along +v
-          const float* body = half ? s2 : s1;
+          const T* body = half ? s2 : s1;
           const int nvb = half ? nv2 : nv1;
-          const V3<float> d = half ? g.v : vneg(g.v);
-          V3<float> sup = half ? g.sup2 : g.sup1;
+          const V3<T> d = half ? g.v : vneg(g.v);
+          V3<T> sup = half ? g.sup2 : g.sup1;
           int sidx = half ? g.idx2 : g.idx1;
           support_slot(body, nvb, d, zero, sup, sidx);
-          const float ox = __shfl_xor_sync(runm, sup.x, 1), oy = __shfl_xor_sync(runm, sup.y, 1),
-                      oz = __shfl_xor_sync(runm, sup.z, 1);
+          const T ox = __shfl_xor_sync(runm, sup.x, 1), oy = __shfl_xor_sync(runm, sup.y, 1),
+                  oz = __shfl_xor_sync(runm, sup.z, 1);
           const int oi = __shfl_xor_sync(runm, sidx, 1);
-          const V3<float> osup = mk<float>(ox, oy, oz);
+          const V3<T> osup = mk<T>(ox, oy, oz);
           g.sup1 = half ? osup : sup;
           g.sup2 = half ? sup : osup;
           g.idx1 = half ? oi : sidx;
@@ -608,15 +678,15 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
         while ((int)(base + cnt - ld_vol(&ring_ctl[1])) > kRingRecords) __nanosleep(64);  // ring full: wait for space
         const unsigned idx = base + __popc(fin & ((1u << (lane & ~(LP - 1))) - 1u));
         if (done) {
-          float* rec = ring + (size_t)(idx % kRingRecords) * kRecWords;
-          const SV<float>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
+          T* rec = ring + (size_t)(idx % kRingRecords) * kRecWords;
+          const SV<T>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
           // all slot reads first, then all record writes: both are shared memory, so the compiler keeps their order
           // and a load placed after a store would wait out its full latency before the next store can issue
-          float vert[4][6];
+          T vert[4][6];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (LP == 1 || (k >> 1) == half) {
-              const SV<float>& q = *sv[k];
+              const SV<T>& q = *sv[k];
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
                 vert[k][c] = s1[3 * q.i1 + c];
@@ -625,8 +695,8 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
             }
           }
           if (half == 0) {
-            rec[0] = __uint_as_float(pair);
-            rec[1] = __int_as_float(g.S.n);
+            rec[0] = rec_from_int(T(0), pair);
+            rec[1] = rec_from_int(T(0), (unsigned)g.S.n);
             rec[2] = g.v.x;
             rec[3] = g.v.y;
             rec[4] = g.v.z;
@@ -634,12 +704,12 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (LP == 1 || (k >> 1) == half) {
-              const SV<float>& q = *sv[k];
+              const SV<T>& q = *sv[k];
               rec[5 + 5 * k + 0] = q.p.x;
               rec[5 + 5 * k + 1] = q.p.y;
               rec[5 + 5 * k + 2] = q.p.z;
-              rec[5 + 5 * k + 3] = __int_as_float(q.i1);
-              rec[5 + 5 * k + 4] = __int_as_float(q.i2);
+              rec[5 + 5 * k + 3] = rec_from_int(T(0), (unsigned)q.i1);
+              rec[5 + 5 * k + 4] = rec_from_int(T(0), (unsigned)q.i2);
 #pragma unroll
               for (int c = 0; c < 6; ++c) rec[25 + 6 * k + c] = vert[k][c];
             }
@@ -744,21 +814,21 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
       }
       __threadfence_block();
       if (lane < c) {
-        const float* rec = ring + (size_t)(idx % kRingRecords) * kRecWords;
-        const unsigned pair = __float_as_uint(rec[0]);
-        GjkState<float> g;
-        g.S.n = __float_as_int(rec[1]);
-        g.v = mk<float>(rec[2], rec[3], rec[4]);
-        SV<float>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
+        const T* rec = ring + (size_t)(idx % kRingRecords) * kRecWords;
+        const unsigned pair = rec_to_uint(rec[0]);
+        GjkState<T> g;
+        g.S.n = (int)rec_to_uint(rec[1]);
+        g.v = mk<T>(rec[2], rec[3], rec[4]);
+        SV<T>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          sv[k]->p = mk<float>(rec[5 + 5 * k], rec[6 + 5 * k], rec[7 + 5 * k]);
+          sv[k]->p = mk<T>(rec[5 + 5 * k], rec[6 + 5 * k], rec[7 + 5 * k]);
           // tag (bits 30..31): which record vertex this slot came with -- survives the witness stage's slot shuffles
-          sv[k]->i1 = (int)(__float_as_uint(rec[8 + 5 * k]) | ((unsigned)k << 30));
-          sv[k]->i2 = (int)(__float_as_uint(rec[9 + 5 * k]) | ((unsigned)k << 30));
+          sv[k]->i1 = (int)(rec_to_uint(rec[8 + 5 * k]) | ((unsigned)k << 30));
+          sv[k]->i2 = (int)(rec_to_uint(rec[9 + 5 * k]) | ((unsigned)k << 30));
         }
-        RecordFetch fetch{rec + 25};
-        V3<float> w1, w2;
+        RecordFetch<T> fetch{rec + 25};
+        V3<T> w1, w2;
         gjk_witnesses(fetch, g.S, w1, w2);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -767,11 +837,11 @@ gjk_slots_ws_kernel(const float* __restrict__ coord1, const float* __restrict__ 
         }
         store_result(simplices + pair, distances + pair, g, w1, w2);
         if (normals) {  // fused EPA gate
-          const float dist = sqrt_rn(norm2(g.v));
-          bool collide = !(dist > Tol<float>::eps());
+          const T dist = sqrt_rn(norm2(g.v));
+          bool collide = !(dist > Tol<T>::eps());
           if (!collide) {
-            const V3<float> nr = normal_from_witnesses(w1, w2);
-            float* o = normals + 3 * (size_t)pair;
+            const V3<T> nr = normal_from_witnesses(w1, w2);
+            T* o = normals + 3 * (size_t)pair;
             o[0] = nr.x;
             o[1] = nr.y;
             o[2] = nr.z;

@@ -5,6 +5,7 @@
 // reference accumulates coordinate counts in `int`, openGJK.cu:2910-2915), pinned staging and stream-ordered
 // copies.  There is deliberately no CPU fallback: without a usable device every compute call fails.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -18,6 +19,7 @@
 #include "epa_kernel.cuh"
 #include "epa_group.cuh"
 #include "broadphase.cuh"
+#include "contact.cuh"
 #include "transform.cuh"
 #include "gjk_generic.cuh"
 #include "gjk_tables.h"
@@ -201,16 +203,17 @@ unsigned slots_prefetch_ahead() {
   return v < 0 ? 0u : (unsigned)v;
 }
 
-int launch_gjk_slots(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist,
+template <typename T>
+int launch_gjk_slots(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist,
                      const CollisionPair* pairs = nullptr) {
   int dev = 0;
   OGJK_CK(cudaGetDevice(&dev));
   const uint16_t* utab = nullptr;
   if (int rc = device_unified_table(&utab)) return rc;
   if (!t_ticket[dev]) OGJK_CK(cudaMalloc(&t_ticket[dev], sizeof(unsigned)));
-  const size_t smem = (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2);
+  const size_t smem = (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2, (int)sizeof(T));
   // the interleaved scan needs ~40 more registers: only where shared memory, not registers, bounds occupancy
-  auto kern = (nv1 == nv2 && nv1 >= 32) ? gjk_slots_kernel<true> : gjk_slots_kernel<false>;
+  auto kern = (sizeof(T) == 4 && nv1 == nv2 && nv1 >= 32) ? gjk_slots_kernel<T, true> : gjk_slots_kernel<T, false>;
   long long grid = 0;
   if (int rc = persistent_grid(kern, kSlotThreads, smem, &grid)) return rc;
   const long long need = ((long long)n + kSlotThreads - 1) / kSlotThreads;
@@ -231,40 +234,42 @@ unsigned ws_dense_chunk() {
 // warp-specialised slot kernel.  Configurations (compute warps, lanes per pair): (8,1) when 256 slots fit an SM;
 // otherwise (8,2) -- 128 slots, two lanes per pair -- or (4,1); (2,1) = 64 slots for 65..~140 vertices per body.  normals/queue/count non-null = fused EPA gate.
 // development override: OGJK_WS_LP=1|2 picks between (4,1) and (8,2) for the 128-slot case.
-int ws_config(int nv1, int nv2, int* lp) {
-  const size_t sb = slot_bytes(nv1, nv2);
+int ws_config(int nv1, int nv2, int* lp, int esize) {
+  const size_t sb = slot_bytes(nv1, nv2, esize);
   *lp = 1;
-  if (ws_fixed_bytes(256) + 256 * sb + kSlotPadBytes <= 227u * 1024u) return 8;
+  if (ws_fixed_bytes(256, esize) + 256 * sb + kSlotPadBytes <= 227u * 1024u) return 8;
   const char* e = getenv("OGJK_WS_LP");
-  if (e && atoi(e) == 2 &&
+  if (e && atoi(e) == 2 && esize == 4 &&
       ws_fixed_bytes(128) + 128 * (size_t)ws_slot_layout(nv1, nv2, 2).stride + kSlotPadBytes <= 227u * 1024u) {
     *lp = 2;
     return 8;
   }
-  if (ws_fixed_bytes(128) + 128 * sb + kSlotPadBytes <= 227u * 1024u) return 4;
-  if (ws_fixed_bytes(64) + 64 * sb + kSlotPadBytes <= 227u * 1024u) return 2;  // 65..~140 vertices per body
+  if (ws_fixed_bytes(128, esize) + 128 * sb + kSlotPadBytes <= 227u * 1024u) return 4;
+  if (ws_fixed_bytes(64, esize) + 64 * sb + kSlotPadBytes <= 227u * 1024u) return 2;  // fp32: 65..~140 vertices per body
   // (one compute warp, 32 slots, up to ~270 vertices per body, was measured too: it loses to gjk_uniform_kernel,
   //  2.0e8 against 3.1e8 pairs/s at 256 vertices, while two compute warps win, 7.3e8 against 4.7e8 at 96 vertices)
   return 0;
 }
-int ws_compute_warps(int nv1, int nv2) {
+int ws_compute_warps(int nv1, int nv2, int esize) {
   int lp;
-  return ws_config(nv1, nv2, &lp);
+  return ws_config(nv1, nv2, &lp, esize);
 }
-template <int CW, int LP>
-int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp,
-                           float* dist, float* nrm, int* queue, int* count, const CollisionPair* pairs) {
+template <typename T, int CW, int LP>
+int launch_gjk_slots_ws_cw(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist, T* nrm,
+                           int* queue, int* count, const CollisionPair* pairs) {
   int dev = 0;
   OGJK_CK(cudaGetDevice(&dev));
   const uint16_t* utab = nullptr;
   if (int rc = device_unified_table(&utab)) return rc;
   if (!t_ticket[dev]) OGJK_CK(cudaMalloc(&t_ticket[dev], sizeof(unsigned)));
   constexpr int nslots = CW * 32 / LP;
-  const size_t smem = (size_t)ws_fixed_bytes(nslots) + kSlotPadBytes + (size_t)nslots * ws_slot_layout(nv1, nv2, LP).stride;
+  constexpr int es = (int)sizeof(T);
+  const size_t smem = (size_t)ws_fixed_bytes(nslots, es) + kSlotPadBytes + (size_t)nslots * ws_slot_layout(nv1, nv2, LP, es).stride;
   constexpr int threads = (CW + 2) * 32;
-  auto kern = pairs ? gjk_slots_ws_kernel<CW, LP, LP == 1, true>  // one pool: equal vertex counts by construction
-                    : (LP == 1 && nv1 == nv2) ? gjk_slots_ws_kernel<CW, LP, true, false>
-                                              : gjk_slots_ws_kernel<CW, LP, false, false>;
+  constexpr bool eq_ok = LP == 1 && es == 4;  // the interleaved two-body scan exists for fp32 only
+  auto kern = pairs ? gjk_slots_ws_kernel<T, CW, LP, eq_ok, true>  // one pool: equal vertex counts by construction
+                    : (eq_ok && nv1 == nv2) ? gjk_slots_ws_kernel<T, CW, LP, eq_ok, false>
+                                            : gjk_slots_ws_kernel<T, CW, LP, false, false>;
   long long grid = 0;
   if (int rc = persistent_grid(kern, threads, smem, &grid)) return rc;
   const long long need = ((long long)n + nslots - 1) / nslots;
@@ -274,40 +279,46 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const float* c1, int nv2, const float
                                                     nrm, queue, count, pairs, ws_dense_chunk());
   return finish_launch("gjk slots (warp-specialised) kernel");
 }
-int launch_gjk_slots_ws(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp, float* dist,
-                        float* nrm, int* queue, int* count, const CollisionPair* pairs = nullptr) {
+template <typename T>
+int launch_gjk_slots_ws(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist, T* nrm,
+                        int* queue, int* count, const CollisionPair* pairs = nullptr) {
   int lp = 1;
-  const int cw = ws_config(nv1, nv2, &lp);
-  if (cw == 8 && lp == 1) return launch_gjk_slots_ws_cw<8, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
-  if (cw == 8 && lp == 2) return launch_gjk_slots_ws_cw<8, 2>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
-  if (cw == 4) return launch_gjk_slots_ws_cw<4, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
-  if (cw == 2) return launch_gjk_slots_ws_cw<2, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  const int cw = ws_config(nv1, nv2, &lp, (int)sizeof(T));
+  if (cw == 8 && lp == 1) return launch_gjk_slots_ws_cw<T, 8, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  if constexpr (sizeof(T) == 4) {
+    if (cw == 8 && lp == 2)
+      return launch_gjk_slots_ws_cw<T, 8, 2>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  }
+  if (cw == 4) return launch_gjk_slots_ws_cw<T, 4, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  if (cw == 2) return launch_gjk_slots_ws_cw<T, 2, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
   return 1;
 }
 
 // policy: the warp-specialised kernel pays off when slots are so large that the self-service kernel would be down
 // to one 4-warp CTA per SM (measured on B200: 64+64 vertices 1.28e9 vs 1.15e9 pairs/s; at 32+32 vertices, where
 // the self-service kernel runs 8 warps per SM, it is the other way round: 1.6e9 vs 2.6e9)
-bool use_ws_kernel(int nv1, int nv2) {
+bool use_ws_kernel(int nv1, int nv2, int esize) {
   const char* e = getenv("OGJK_WS_MIN_SLOT");  // development override (bytes)
   const int thr = e ? atoi(e) : 880;
-  return ws_compute_warps(nv1, nv2) != 0 && (int)slot_bytes(nv1, nv2) >= thr;
+  if (ws_compute_warps(nv1, nv2, esize) == 0) return false;
+  // fp64 (measured on B200, 1 Mi pairs): the self-service kernel wins wherever its 128 slots fit -- 32+32 vertices
+  // 1.06 ms against 1.45 ms, 16+16 0.53 against 0.78 -- so the warp-specialised kernel (64 slots) only takes over
+  // above that: 64+64 vertices 1.99 ms against 2.14 ms for the general kernel
+  if (esize == 8 && !e)
+    return (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2, esize) > 227u * 1024u;
+  return (int)slot_bytes(nv1, nv2, esize) >= thr;
 }
 
 template <typename T>
-int launch_gjk_slots_if(int, int, const T*, int, const T*, SimplexT<T>*, T*) {
-  return 1;
-}
-template <>
-int launch_gjk_slots_if<float>(int n, int nv1, const float* c1, int nv2, const float* c2, SimplexT<float>* simp,
-                               float* dist) {
+int launch_gjk_slots_if(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist) {
+  constexpr int es = (int)sizeof(T);
   const int force = forced_kernel();
   if (force == 2 || force == 3) return 1;
-  if (force == 4 || (force == 0 && n >= 32768 && use_ws_kernel(nv1, nv2)))
-    return launch_gjk_slots_ws(n, nv1, c1, nv2, c2, simp, dist, nullptr, nullptr, nullptr);
-  if ((size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2) > 227u * 1024u) return 1;
+  if (force == 4 || (force == 0 && n >= 32768 && use_ws_kernel(nv1, nv2, es)))
+    return launch_gjk_slots_ws<T>(n, nv1, c1, nv2, c2, simp, dist, nullptr, nullptr, nullptr);
+  if ((size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2, es) > 227u * 1024u) return 1;
   if (force == 0 && n < 32768) return 1;
-  return launch_gjk_slots(n, nv1, c1, nv2, c2, simp, dist);
+  return launch_gjk_slots<T>(n, nv1, c1, nv2, c2, simp, dist);
 }
 
 template <typename T>
@@ -449,16 +460,16 @@ int launch_gjk_epa_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, Si
   if (!nrm) return fail_msg("contact_normals must not be NULL on the device path");
   UniformSource<T> src{c1, c2, nv1, nv2};
   if (int rc = stage_mark(0)) return rc;
-  if constexpr (sizeof(T) == 4) {
+  {
     const bool aligned = (((uintptr_t)c1 | (uintptr_t)c2) & 15u) == 0 && nv1 % 4 == 0 && nv2 % 4 == 0;
     const int force = forced_kernel();
-    if (aligned && n >= 32768 && (force == 0 || force == 4) && use_ws_kernel(nv1, nv2)) {
+    if (aligned && n >= 32768 && (force == 0 || force == 4) && use_ws_kernel(nv1, nv2, (int)sizeof(T))) {
       int* scratch = nullptr;
       if (int rc = epa_scratch((size_t)n + 2, &scratch)) return rc;
       OGJK_CK(cudaMemsetAsync(scratch, 0, 2 * sizeof(int), t_stream));
       const bool sync_saved = t_sync;
       t_sync = false;  // no need to synchronise between the two stages
-      int rc = launch_gjk_slots_ws(n, nv1, c1, nv2, c2, simp, dist, nrm, scratch + 2, scratch);
+      int rc = launch_gjk_slots_ws<T>(n, nv1, c1, nv2, c2, simp, dist, nrm, scratch + 2, scratch);
       t_sync = sync_saved;
       if (!rc) rc = stage_mark(1);
       if (!rc) rc = launch_epa_queue<T, UniformSource<T>>(src, n, simp, dist, nrm, scratch + 2, scratch);
@@ -516,28 +527,24 @@ bool lookup_pool(const void* d_desc, PoolInfo* out) {
 // GJK (and optionally the fused EPA gate + EPA) over `pairs` into a uniform fp32 pool.  Returns 1 when the batch does
 // not qualify for the slot kernels.
 template <typename T>
-int launch_indexed_uniform(int, const PoolInfo&, const CollisionPair*, const PolytopeT<T>*, SimplexT<T>*, T*, T*, int) {
-  return 1;
-}
-template <>
-int launch_indexed_uniform<float>(int n, const PoolInfo& pool, const CollisionPair* d_pairs,
-                                  const PolytopeT<float>* d_desc, SimplexT<float>* simp, float* dist, float* nrm,
-                                  int stages) {
+int launch_indexed_uniform(int n, const PoolInfo& pool, const CollisionPair* d_pairs, const PolytopeT<T>* d_desc,
+                           SimplexT<T>* simp, T* dist, T* nrm, int stages) {
+  constexpr int es = (int)sizeof(T);
   const int nv = pool.nv;
-  const float* base = (const float*)pool.coords;
+  const T* base = (const T*)pool.coords;
   const int force = forced_kernel();
   if (nv <= 0 || nv % 4 || n < 32768 || force == 2 || force == 3 || !(stages & kGjkStage)) return 1;
-  const bool ws = force == 4 || (force == 0 && use_ws_kernel(nv, nv));
-  const bool v2_fits = (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv, nv) <= 227u * 1024u;
+  const bool ws = force == 4 || (force == 0 && use_ws_kernel(nv, nv, es));
+  const bool v2_fits = (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv, nv, es) <= 227u * 1024u;
   if (!ws && !v2_fits) return 1;
-  if (ws && ws_compute_warps(nv, nv) == 0) return 1;
+  if (ws && ws_compute_warps(nv, nv, es) == 0) return 1;
   const bool epa = (stages & kEpaStage) != 0;
   if (!epa) {
-    return ws ? launch_gjk_slots_ws(n, nv, base, nv, base, simp, dist, nullptr, nullptr, nullptr, d_pairs)
-              : launch_gjk_slots(n, nv, base, nv, base, simp, dist, d_pairs);
+    return ws ? launch_gjk_slots_ws<T>(n, nv, base, nv, base, simp, dist, nullptr, nullptr, nullptr, d_pairs)
+              : launch_gjk_slots<T>(n, nv, base, nv, base, simp, dist, d_pairs);
   }
   if (!nrm) return fail_msg("contact_normals must not be NULL on the device path");
-  IndexedSource<float> src{d_desc, d_pairs};
+  IndexedSource<T> src{d_desc, d_pairs};
   const bool sync_saved = t_sync;
   t_sync = false;
   int rc;
@@ -552,14 +559,14 @@ int launch_indexed_uniform<float>(int n, const PoolInfo& pool, const CollisionPa
       t_sync = sync_saved;
       return fail("cudaMemsetAsync", e);
     }
-    rc = launch_gjk_slots_ws(n, nv, base, nv, base, simp, dist, nrm, scratch + 2, scratch, d_pairs);
+    rc = launch_gjk_slots_ws<T>(n, nv, base, nv, base, simp, dist, nrm, scratch + 2, scratch, d_pairs);
     t_sync = sync_saved;
-    if (!rc) rc = launch_epa_queue<float, IndexedSource<float>>(src, n, simp, dist, nrm, scratch + 2, scratch);
+    if (!rc) rc = launch_epa_queue<T, IndexedSource<T>>(src, n, simp, dist, nrm, scratch + 2, scratch);
     return rc;
   }
-  rc = launch_gjk_slots(n, nv, base, nv, base, simp, dist, d_pairs);
+  rc = launch_gjk_slots<T>(n, nv, base, nv, base, simp, dist, d_pairs);
   t_sync = sync_saved;
-  if (!rc) rc = launch_epa<float>(src, n, simp, dist, nrm);
+  if (!rc) rc = launch_epa<T>(src, n, simp, dist, nrm);
   return rc;
 }
 
@@ -1017,6 +1024,68 @@ int broadphase_pairs(int n, const float4* d_pos, float cell_size, float boundary
   return 0;
 }
 
+// ---- contact response (reference visualization/integrate_final_gjk.cu:572-689, 1039-1054) ---
+thread_local Scratch t_cr_scratch[kMaxDevices];
+
+template <typename T>
+int contact_response(int num_pairs, const CollisionPair* d_pairs, const T* d_dist, const SimplexT<T>* d_simp,
+                     const T* d_nrm, const int* d_sub_mesh_body, int num_objects, float4* d_pos, const float4* d_vel_ping,
+                     float4* d_vel_pong, const float4* d_ang_ping, float4* d_ang_pong, const float4* d_quats,
+                     const float* d_inv_inertia, ContactParams prm) {
+  if (num_objects <= 0) return 0;
+  if (num_pairs < 0) num_pairs = 0;
+  if (!d_pos || !d_vel_ping || !d_vel_pong || !d_ang_ping || !d_ang_pong || !d_quats || !d_inv_inertia)
+    return fail_msg("null argument");
+  if (num_pairs > 0 && (!d_pairs || !d_dist || !d_simp || !d_nrm)) return fail_msg("null argument");
+  if (d_vel_ping == d_vel_pong || d_ang_ping == d_ang_pong) return fail_msg("ping and pong buffers must differ");
+  if (num_pairs > (1 << 30)) return fail_msg("too many pairs");
+  int dev = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail_msg("device ordinal out of range");
+  const size_t slots = 2 * (size_t)num_pairs;
+  int key_bits = 1;
+  while ((1ll << key_bits) <= (long long)num_objects) ++key_bits;  // the sentinel key is num_objects itself
+  size_t sort_bytes = 0;
+  if (slots)
+    OGJK_CK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                            (const unsigned*)nullptr, (unsigned*)nullptr, (int)slots, 0, key_bits,
+                                            t_stream));
+  // counts[num_objects + 1] | seg_start[num_objects + 2] | keys[slots] x 2 | slot ids[slots] x 2 | positions_out | sort temp
+  const size_t head = 2 * (size_t)num_objects + 4;
+  const size_t ints = head + 4 * slots + 4 * (size_t)num_objects + (sort_bytes + 3) / 4 + 8;
+  Scratch& sc = t_cr_scratch[dev];
+  if (sc.ints < ints) {
+    if (sc.ptr) cudaFree(sc.ptr);
+    sc.ptr = nullptr;
+    sc.ints = 0;
+    OGJK_CK(cudaMalloc(&sc.ptr, ints * sizeof(int)));
+    sc.ints = ints;
+  }
+  int* counts = sc.ptr;
+  int* seg_start = counts + num_objects + 1;
+  unsigned* keys_in = (unsigned*)(sc.ptr + ((head + 3) & ~(size_t)3));
+  unsigned* keys_out = keys_in + slots;
+  unsigned* slots_in = keys_out + slots;
+  unsigned* slots_out = slots_in + slots;
+  float4* pos_out = (float4*)(((uintptr_t)(slots_out + slots) + 15u) & ~(uintptr_t)15u);
+  void* sort_tmp = (void*)(pos_out + num_objects);
+  OGJK_CK(cudaMemsetAsync(counts, 0, ((size_t)num_objects + 1) * sizeof(int), t_stream));
+  if (num_pairs > 0) {
+    cr_keys_kernel<T><<<(unsigned)((num_pairs + 255) / 256), 256, 0, t_stream>>>(
+        d_pairs, d_dist, d_sub_mesh_body, prm.epsilon, num_pairs, num_objects, keys_in, slots_in, counts);
+    ++t_launches;
+    OGJK_CK(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys_in, keys_out, slots_in, slots_out, (int)slots, 0,
+                                            key_bits, t_stream));
+  }
+  bp_exclusive_scan_kernel<<<1, 1024, 0, t_stream>>>(counts, seg_start, num_objects);
+  ++t_launches;
+  cr_accumulate_kernel<T><<<(unsigned)(((long long)num_objects * 32 + 255) / 256), 256, 0, t_stream>>>(
+      d_pos, pos_out, d_vel_ping, d_vel_pong, d_ang_ping, d_ang_pong, d_quats, d_inv_inertia, d_pairs, d_dist, d_simp,
+      d_nrm, d_sub_mesh_body, prm, num_objects, seg_start, slots_out);
+  OGJK_CK(cudaMemcpyAsync(d_pos, pos_out, (size_t)num_objects * sizeof(float4), cudaMemcpyDeviceToDevice, t_stream));
+  return finish_launch("contact response");
+}
+
 }  // namespace
 
 // =======================================================================================================
@@ -1292,6 +1361,20 @@ long long ogjk_launch_count(int reset) {
     if (uniform && uniform_count % 4 == 0 && ((uintptr_t)d_verts_world & 15u) == 0)                                    \
       register_pool(d_polytopes, d_verts_world, uniform_count, num_submeshes);                                         \
     return finish_launch("init_polytopes");                                                                            \
+  }                                                                                                                    \
+  int ogjk_##P##_contact_response_device(int num_pairs, const void* d_pairs, const REAL* d_distances,                  \
+                                         const void* d_simplices, const REAL* d_contact_normals,                       \
+                                         const int* d_sub_mesh_body, int num_objects, float* d_positions,              \
+                                         const float* d_vel_ping, float* d_vel_pong, const float* d_ang_ping,          \
+                                         float* d_ang_pong, const float* d_quats, const float* d_inv_inertia,          \
+                                         const float* params) {                                                        \
+    if (!params) return fail_msg("null argument");                                                                     \
+    const ContactParams prm{params[0], params[1], params[2], params[3]};                                               \
+    return contact_response<REAL>(num_pairs, (const CollisionPair*)d_pairs, d_distances,                               \
+                                  (const SimplexT<REAL>*)d_simplices, d_contact_normals, d_sub_mesh_body, num_objects, \
+                                  (float4*)d_positions, (const float4*)d_vel_ping, (float4*)d_vel_pong,                \
+                                  (const float4*)d_ang_ping, (float4*)d_ang_pong, (const float4*)d_quats,              \
+                                  d_inv_inertia, prm);                                                                 \
   }                                                                                                                    \
   int ogjk_##P##_gjk_uniform_device(int n, int nverts1, const REAL* d_coord1, int nverts2, const REAL* d_coord2,      \
                                     void* d_simplices, REAL* d_distances) {                                           \

@@ -9,12 +9,13 @@ nv = int(sys.argv[1]); spread = float(sys.argv[2])
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 20
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 epa = len(sys.argv) > 5 and sys.argv[5] == 'epa'
-dtype = np.float32
+dtype = np.float64 if os.environ.get('OGJK_F64') else np.float32
+tdt = torch.float64 if dtype == np.float64 else torch.float32
 eng = pkg.Engine(dtype); eng.set_device(0); eng.set_sync(False)
 a, b = pkg.workloads.random_pairs(n, nv, spread, seed=12345, dtype=dtype)
 da = torch.from_numpy(a).cuda(); db = torch.from_numpy(b).cuda()
 simp = torch.zeros(n * eng.sdtype.itemsize, dtype=torch.uint8, device='cuda')
-dist = torch.zeros(n, dtype=torch.float32, device='cuda'); nrm = torch.zeros(n, 3, dtype=torch.float32, device='cuda')
+dist = torch.zeros(n, dtype=tdt, device='cuda'); nrm = torch.zeros(n, 3, dtype=tdt, device='cuda')
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
 ts = []
 for _ in range(reps):
@@ -22,4 +23,4 @@ for _ in range(reps):
     e0.record(); eng.gjk_uniform_device(n, nv, da, nv, db, simp, dist)
     if epa: eng.epa_uniform_device(n, nv, da, nv, db, simp, dist, nrm)
     e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-print(f"kernel={os.environ.get('OGJK_GJK_KERNEL','auto')} n={n} V={nv} S={spread} epa={epa}: min {min(ts):.3f} ms {n/min(ts)*1e3:.3e} pairs/s", flush=True)
+print(f"{np.dtype(dtype).name} kernel={os.environ.get('OGJK_GJK_KERNEL','auto')} n={n} V={nv} S={spread} epa={epa}: min {min(ts):.3f} ms {n/min(ts)*1e3:.3e} pairs/s", flush=True)

@@ -33,10 +33,11 @@ def _device_batch(pkg, a, b, dtype=np.float32):
     n = a.shape[0]
     eng = pkg.Engine(dtype)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
     d_a, d_b = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     d_simp = torch.zeros(n * eng.sdtype.itemsize, dtype=torch.uint8, device="cuda")
-    d_dist = torch.zeros(n, dtype=torch.float32, device="cuda")
-    d_nrm = torch.zeros(n, 3, dtype=torch.float32, device="cuda")
+    d_dist = torch.zeros(n, dtype=tdt, device="cuda")
+    d_nrm = torch.zeros(n, 3, dtype=tdt, device="cuda")
     return eng, d_a, d_b, d_simp, d_dist, d_nrm
 
 
@@ -74,6 +75,33 @@ def test_ws_two_lanes_per_pair(pkg, oracle_mod, force_kernel, nv1, nv2, spread):
     os_, od = oracle_mod.Oracle("port", np.float32).gjk(a, b, nthreads=8)
     assert np.array_equal(d_dist.cpu().numpy(), od)
     assert live_simplex_equal(d_simp.cpu().numpy().view(eng.sdtype), os_)
+    eng.set_stream(0)
+
+
+@pytest.mark.parametrize("kernel", ["slots", "slotsws", "auto"])
+@pytest.mark.parametrize("nv1,nv2,spread", [(64, 64, 10.0), (32, 32, 1.0), (16, 16, 3.0), (8, 8, 10.0), (24, 40, 4.0),
+                                            (48, 48, 0.5), (4, 4, 2.0)])
+def test_slot_kernels_fp64(pkg, oracle_mod, force_kernel, kernel, nv1, nv2, spread):
+    """the slot kernels in double precision (96-byte vertex blocks, scalar DMUL/DADD scan)"""
+    import torch
+    n = 40000
+    a = pkg.workloads.random_polytopes(n, nv1, spread, 31, np.float64, stream=1)
+    b = pkg.workloads.random_polytopes(n, nv2, spread, 31, np.float64, stream=2)
+    eng, d_a, d_b, d_simp, d_dist, d_nrm = _device_batch(pkg, a, b, np.float64)
+    force_kernel(kernel)
+    orc = oracle_mod.Oracle("port", np.float64)
+    os_, od = orc.gjk(a, b, nthreads=8)
+    eng.gjk_uniform_device(n, nv1, d_a, nv2, d_b, d_simp, d_dist)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_dist.cpu().numpy(), od)
+    assert live_simplex_equal(d_simp.cpu().numpy().view(eng.sdtype), os_)
+    if nv1 == nv2:  # fused GJK + EPA entry (finisher-warp gate when the ws kernel is taken)
+        eng.gjk_epa_uniform_device(n, nv1, d_a, nv2, d_b, d_simp, d_dist, d_nrm)
+        torch.cuda.synchronize()
+        es, ed, en = orc.epa(a, b, os_, od, nthreads=8)
+        assert np.array_equal(d_dist.cpu().numpy(), ed)
+        assert np.array_equal(d_nrm.cpu().numpy(), en)
+        assert live_simplex_equal(d_simp.cpu().numpy().view(eng.sdtype), es)
     eng.set_stream(0)
 
 
