@@ -615,7 +615,17 @@ gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, 
     uint32_t parity = 0;
     unsigned pair = 0;
     GjkState<T> g;
+    // The loop is ROTATED: a trip is [sub-algorithm step of the iteration begun last trip] -> [take a new pair if the
+    // slot has been refilled] -> [support scans + the two exit pre-tests of the next iteration] -> [retire].  Most
+    // pairs end at the pre-tests (every separated pair does), so their slot is handed back right after the scans and
+    // the refill overlaps the other lanes' sub-algorithm step.  The arithmetic per pair is the same sequence as in
+    // gjk_advance_u.  (Measured: 0.769 against 0.774 ms on config 2 -- the refill, ~2 us from HBM, is still longer
+    // than the sub-algorithm step, profiles/r1e_experiments.txt.)
+    bool need_sub = false;  // this lane passed the pre-tests last trip and owes the sub-algorithm step
     for (;;) {
+      bool fin_sub = false;
+      if (state == kRun && need_sub) fin_sub = gjk_substep_u(g, utab);
+      need_sub = false;
       if (state == kWait) {
         if (mbar_test_wait(bar, parity)) {
           parity ^= 1u;
@@ -635,9 +645,9 @@ gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, 
       }
       if (__all_sync(0xffffffffu, state == kExit)) break;
       if (!__any_sync(0xffffffffu, state == kRun)) __nanosleep(32);  // start-up / drain: nothing loaded yet
-      bool finished = false;
-      const unsigned runm = __ballot_sync(0xffffffffu, state == kRun);  // both lanes of a pair are in it, or neither
-      if (state == kRun) {
+      bool finished = fin_sub;
+      const unsigned runm = __ballot_sync(0xffffffffu, state == kRun && !fin_sub);  // both lanes of a pair, or neither
+      if (state == kRun && !fin_sub) {
         ++g.k;
         if (LP == 1) {
           if (EQ) {
@@ -663,11 +673,13 @@ gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, 
           g.idx1 = half ? oi : sidx;
           g.idx2 = half ? sidx : oi;
         }
-        finished = gjk_advance_u(g, utab);
+        finished = gjk_converged_u(g);
+        need_sub = !finished;
       }
-      // (Retiring the pairs that end at the pre-tests before the others run the sub-algorithm, and pulling upcoming
-      // pairs into L2 with cp.async.bulk.prefetch from the loader, were both measured and both lost: 1.30e9 and
-      // 0.98-1.15e9 pairs/s against 1.36e9 -- profiles/r1_gjk_kernels_ab.txt.)
+      // (Measured and dropped: a second retire call site in front of the sub-algorithm; pulling upcoming pairs into L2
+      // -- cp.async.bulk.prefetch.L2 or per-line prefetch.global.L2 from the loader, any distance; staging buffers
+      // behind the slots; extra compute warps with register-resident pairs.  profiles/r1c_gjk_kernels_ab.txt,
+      // profiles/r1e_experiments.txt.)
       auto retire = [&](bool done) {
         const unsigned fin = __ballot_sync(0xffffffffu, done && half == 0);
         if (!fin) return;
@@ -740,7 +752,7 @@ gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, 
     unsigned exited = 0;               // bit j: slot lane + 32 j has been told to exit
     for (;;) {
       bool any = false;
-#pragma unroll
+#pragma unroll  // (a rolled loop makes the kernel 11 % smaller but each poll slower: 0.781 against 0.769 ms)
       for (int j = 0; j < kSlots / 32; ++j) {
         const int s = lane + 32 * j;
         bool want = !((exited >> j) & 1u) && ld_vol(&ctrl[s]) == kSlotFree;
