@@ -1,0 +1,165 @@
+"""GPU parity on DEGENERATE geometry: the inputs on which a support scan's tie-break, the sub-algorithm's sign
+predicates and the witness stage's demotions actually matter -- duplicated vertices, point / segment / planar
+bodies, integer-lattice cubes that touch or coincide exactly, identical bodies, very small and very large scales.
+Every kernel family must reproduce the CPU reference bit for bit on these too (the reference's own tests only hold
+the cube cases, examples/main.cpp and EPATesting).  The oracle here is the reference's own CPU
+code where it was compiled (oracle/_ref), else the C restatement."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import live_simplex_equal
+
+pytestmark = pytest.mark.gpu
+
+CATEGORIES = ["duplicates", "point_vs_cloud", "collinear", "coplanar", "lattice_cubes", "identical", "tiny", "large"]
+
+
+def degenerate_pairs(n, nv, seed, dtype=np.float32):
+    """[n, nv, 3] x 2; pair i belongs to category i % len(CATEGORIES)"""
+    rng = np.random.Generator(np.random.Philox(key=[seed, 77]))
+    a = np.zeros((n, nv, 3), dtype=np.float64)
+    b = np.zeros((n, nv, 3), dtype=np.float64)
+    cat = np.arange(n) % len(CATEGORIES)
+    cube = np.array([[x, y, z] for x in (0, 1) for y in (0, 1) for z in (0, 1)], dtype=np.float64)
+
+    def cloud(m, k, spread):
+        return rng.normal(size=(m, k, 3)) + (rng.random((m, 1, 3)) - 0.5) * spread
+
+    for c, name in enumerate(CATEGORIES):
+        idx = np.nonzero(cat == c)[0]
+        m = idx.size
+        if name == "duplicates":  # 8 distinct points, each repeated: every support scan ends in an exact tie
+            pa, pb = cloud(m, 8, 4.0), cloud(m, 8, 4.0)
+            pick = rng.integers(0, 8, size=(m, nv))
+            a[idx] = np.take_along_axis(pa, pick[..., None].repeat(3, -1), axis=1)
+            pick = rng.integers(0, 8, size=(m, nv))
+            b[idx] = np.take_along_axis(pb, pick[..., None].repeat(3, -1), axis=1)
+        elif name == "point_vs_cloud":
+            a[idx] = cloud(m, 1, 6.0).repeat(nv, axis=1)
+            b[idx] = cloud(m, nv, 6.0)
+        elif name == "collinear":
+            p, d = cloud(m, 1, 4.0), rng.normal(size=(m, 1, 3))
+            a[idx] = p + d * rng.integers(-4, 5, size=(m, nv, 1))
+            b[idx] = cloud(m, nv, 4.0)
+        elif name == "coplanar":
+            a[idx] = cloud(m, nv, 3.0)
+            a[idx, :, 2] = np.round(a[idx, :1, 2])
+            b[idx] = cloud(m, nv, 3.0)
+            b[idx, :, 0] = np.round(b[idx, :1, 0])
+        elif name == "lattice_cubes":  # unit cubes on the integer lattice: touching faces / edges / corners, overlaps
+            rep = cube[rng.integers(0, 8, size=(m, nv))]
+            rep[:, :8] = cube
+            a[idx] = rep
+            shift = rng.integers(-2, 3, size=(m, 1, 3)).astype(np.float64)
+            rep = cube[rng.integers(0, 8, size=(m, nv))]
+            rep[:, :8] = cube[::-1]
+            b[idx] = rep + shift
+        elif name == "identical":
+            a[idx] = cloud(m, nv, 2.0)
+            b[idx] = a[idx]
+        elif name == "tiny":
+            a[idx] = cloud(m, nv, 4.0) * 1e-6
+            b[idx] = cloud(m, nv, 4.0) * 1e-6
+        elif name == "large":
+            a[idx] = cloud(m, nv, 4.0) * 1e6
+            b[idx] = cloud(m, nv, 4.0) * 1e6
+    return a.astype(dtype), b.astype(dtype), cat
+
+
+def _report(cat, bad):
+    return {CATEGORIES[c]: int(np.count_nonzero(bad & (cat == c))) for c in range(len(CATEGORIES)) if np.any(bad & (cat == c))}
+
+
+@pytest.fixture
+def force_kernel():
+    saved = os.environ.get("OGJK_GJK_KERNEL")
+
+    def setter(name):
+        if name == "auto":
+            os.environ.pop("OGJK_GJK_KERNEL", None)
+        else:
+            os.environ["OGJK_GJK_KERNEL"] = name
+
+    yield setter
+    if saved is None:
+        os.environ.pop("OGJK_GJK_KERNEL", None)
+    else:
+        os.environ["OGJK_GJK_KERNEL"] = saved
+
+
+def _oracle(oracle_mod, dtype):
+    kind = "ref" if oracle_mod.available("ref", dtype) else "port"
+    return oracle_mod.Oracle(kind, dtype)
+
+
+@pytest.mark.parametrize("kernel", ["slotsws", "slots", "uniform", "generic"])
+@pytest.mark.parametrize("nv", [64, 32, 8])
+def test_gjk_degenerate_fp32(pkg, oracle_mod, force_kernel, kernel, nv):
+    import torch
+    if kernel == "uniform" and nv <= 16:
+        pytest.skip("the register-resident kernel is not used below 17 vertices")
+    n = 40000
+    a, b, cat = degenerate_pairs(n, nv, seed=5 + nv)
+    eng = pkg.Engine(np.float32)
+    d_a, d_b = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    d_simp = torch.zeros(n * eng.sdtype.itemsize, dtype=torch.uint8, device="cuda")
+    d_dist = torch.zeros(n, dtype=torch.float32, device="cuda")
+    force_kernel(kernel)
+    eng.gjk_uniform_device(n, nv, d_a, nv, d_b, d_simp, d_dist)
+    torch.cuda.synchronize()
+    os_, od = _oracle(oracle_mod, np.float32).gjk(a, b, nthreads=8)
+    got = d_simp.cpu().numpy().view(eng.sdtype)
+    gd = d_dist.cpu().numpy()
+    bad = ~((gd == od) | (np.isnan(gd) & np.isnan(od)))
+    bad |= got["nvrtx"] != os_["nvrtx"]
+    bad |= ~np.all((got["witnesses"] == os_["witnesses"]) | (np.isnan(got["witnesses"]) & np.isnan(os_["witnesses"])), axis=(1, 2))
+    assert not bad.any(), _report(cat, bad)
+    assert live_simplex_equal(got, os_)
+
+
+@pytest.mark.parametrize("nv", [64, 32])
+def test_gjk_degenerate_fp64(pkg, oracle_mod, force_kernel, nv):
+    import torch
+    n = 40000
+    a, b, cat = degenerate_pairs(n, nv, seed=9 + nv, dtype=np.float64)
+    eng = pkg.Engine(np.float64)
+    d_a, d_b = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    d_simp = torch.zeros(n * eng.sdtype.itemsize, dtype=torch.uint8, device="cuda")
+    d_dist = torch.zeros(n, dtype=torch.float64, device="cuda")
+    force_kernel("auto")
+    eng.gjk_uniform_device(n, nv, d_a, nv, d_b, d_simp, d_dist)
+    torch.cuda.synchronize()
+    os_, od = _oracle(oracle_mod, np.float64).gjk(a, b, nthreads=8)
+    got = d_simp.cpu().numpy().view(eng.sdtype)
+    gd = d_dist.cpu().numpy()
+    bad = ~((gd == od) | (np.isnan(gd) & np.isnan(od)))
+    bad |= got["nvrtx"] != os_["nvrtx"]
+    assert not bad.any(), _report(cat, bad)
+    assert live_simplex_equal(got, os_)
+
+
+@pytest.mark.parametrize("nv", [64, 32])
+def test_gjk_epa_degenerate_fused(pkg, oracle_mod, force_kernel, nv):
+    """GJK + EPA through the fused device entry (slot kernel + gate + EPA queue kernel) on the same degenerate set"""
+    import torch
+    n = 40000
+    a, b, cat = degenerate_pairs(n, nv, seed=21 + nv)
+    eng = pkg.Engine(np.float32)
+    d_a, d_b = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    d_simp = torch.zeros(n * eng.sdtype.itemsize, dtype=torch.uint8, device="cuda")
+    d_dist = torch.zeros(n, dtype=torch.float32, device="cuda")
+    d_nrm = torch.zeros(n, 3, dtype=torch.float32, device="cuda")
+    force_kernel("auto")
+    eng.gjk_epa_uniform_device(n, nv, d_a, nv, d_b, d_simp, d_dist, d_nrm)
+    torch.cuda.synchronize()
+    orc = _oracle(oracle_mod, np.float32)
+    s, d = orc.gjk(a, b, nthreads=8)
+    s, d, nr = orc.epa(a, b, s, d, nthreads=8)
+    gd, gn = d_dist.cpu().numpy(), d_nrm.cpu().numpy()
+    got = d_simp.cpu().numpy().view(eng.sdtype)
+    bad = ~((gd == d) | (np.isnan(gd) & np.isnan(d)))
+    bad |= ~np.all((gn == nr) | (np.isnan(gn) & np.isnan(nr)), axis=1)
+    bad |= ~np.all((got["witnesses"] == s["witnesses"]) | (np.isnan(got["witnesses"]) & np.isnan(s["witnesses"])), axis=(1, 2))
+    assert not bad.any(), _report(cat, bad)
