@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 CATEGORIES = ["duplicates", "point_vs_cloud", "collinear", "coplanar", "lattice_cubes", "identical", "tiny", "large"]
 
 
-def degenerate_pairs(n, nv, seed, dtype=np.float32):
+def degenerate_pairs(n, nv, seed, dtype=np.float32, large=1e6):
     """[n, nv, 3] x 2; pair i belongs to category i % len(CATEGORIES)"""
     rng = np.random.Generator(np.random.Philox(key=[seed, 77]))
     a = np.zeros((n, nv, 3), dtype=np.float64)
@@ -63,8 +63,8 @@ def degenerate_pairs(n, nv, seed, dtype=np.float32):
             a[idx] = cloud(m, nv, 4.0) * 1e-6
             b[idx] = cloud(m, nv, 4.0) * 1e-6
         elif name == "large":
-            a[idx] = cloud(m, nv, 4.0) * 1e6
-            b[idx] = cloud(m, nv, 4.0) * 1e6
+            a[idx] = cloud(m, nv, 4.0) * large
+            b[idx] = cloud(m, nv, 4.0) * large
     return a.astype(dtype), b.astype(dtype), cat
 
 
@@ -142,10 +142,17 @@ def test_gjk_degenerate_fp64(pkg, oracle_mod, force_kernel, nv):
 
 @pytest.mark.parametrize("nv", [64, 32])
 def test_gjk_epa_degenerate_fused(pkg, oracle_mod, force_kernel, nv):
-    """GJK + EPA through the fused device entry (slot kernel + gate + EPA queue kernel) on the same degenerate set"""
+    """GJK + EPA through the fused device entry (slot kernel + gate + EPA queue kernel) on the same degenerate set.
+
+    The reference's EPA support search starts from the sentinel -1e10 (GJK/cpu/EPA.c:311-312): when every vertex of a
+    body projects below it -- coordinates ~1e6 against a search direction that is a cross product of such edges -- no
+    vertex is selected and the caller goes on with an UNINITIALISED point and index pair (:338-344, 452-483).  There
+    the reference's output is not a function of its input (its two CPU builds here, oracle/_ref and the C
+    restatement, return different garbage), so the 'large' category is scaled to 1e3 for EPA, and any pair on which
+    the two CPU builds still disagree is excluded and counted."""
     import torch
     n = 40000
-    a, b, cat = degenerate_pairs(n, nv, seed=21 + nv)
+    a, b, cat = degenerate_pairs(n, nv, seed=21 + nv, large=1e3)
     eng = pkg.Engine(np.float32)
     d_a, d_b = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     d_simp = torch.zeros(n * eng.sdtype.itemsize, dtype=torch.uint8, device="cuda")
@@ -154,12 +161,22 @@ def test_gjk_epa_degenerate_fused(pkg, oracle_mod, force_kernel, nv):
     force_kernel("auto")
     eng.gjk_epa_uniform_device(n, nv, d_a, nv, d_b, d_simp, d_dist, d_nrm)
     torch.cuda.synchronize()
-    orc = _oracle(oracle_mod, np.float32)
-    s, d = orc.gjk(a, b, nthreads=8)
-    s, d, nr = orc.epa(a, b, s, d, nthreads=8)
+
+    def run(kind):
+        orc = oracle_mod.Oracle(kind, np.float32)
+        s, d = orc.gjk(a, b, nthreads=8)
+        return orc.epa(a, b, s, d, nthreads=8)
+
+    def differs(x, y):
+        return ~np.all(((x == y) | (np.isnan(x) & np.isnan(y))).reshape(n, -1), axis=1)
+
+    s, d, nr = run("port")
+    defined = np.ones(n, dtype=bool)
+    if oracle_mod.available("ref", np.float32):
+        s2, d2, nr2 = run("ref")
+        defined = ~(differs(d, d2) | differs(nr, nr2) | differs(s["witnesses"], s2["witnesses"]))
+        assert np.count_nonzero(~defined) <= n // 1000, _report(cat, ~defined)
     gd, gn = d_dist.cpu().numpy(), d_nrm.cpu().numpy()
     got = d_simp.cpu().numpy().view(eng.sdtype)
-    bad = ~((gd == d) | (np.isnan(gd) & np.isnan(d)))
-    bad |= ~np.all((gn == nr) | (np.isnan(gn) & np.isnan(nr)), axis=1)
-    bad |= ~np.all((got["witnesses"] == s["witnesses"]) | (np.isnan(got["witnesses"]) & np.isnan(s["witnesses"])), axis=(1, 2))
+    bad = (differs(gd, d) | differs(gn, nr) | differs(got["witnesses"], s["witnesses"])) & defined
     assert not bad.any(), _report(cat, bad)

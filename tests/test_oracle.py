@@ -82,3 +82,26 @@ def test_ragged_and_indexed_drivers(oracle_mod, pkg, dtype):
     if oracle_mod.available("ref", dtype):
         s3, d3, n3 = oracle_mod.Oracle("ref", dtype).gjk_epa_indexed(flat, pairs, off)
         assert np.array_equal(d, d3) and np.array_equal(nrm, n3) and live_simplex_equal(s, s3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("nv", [8, 32])
+def test_port_equals_reference_on_degenerate_geometry(oracle_mod, dtype, nv):
+    """duplicated vertices, point / segment / planar bodies, lattice cubes, identical bodies, tiny and large scales
+    (generator shared with tests/test_gpu_degenerate.py).  EPA is compared at scale 1e3: at 1e6 the reference's EPA
+    support search falls below its -1e10 sentinel and continues with an uninitialised point (GJK/cpu/EPA.c:311-344),
+    so its output there is not a function of its input."""
+    if not oracle_mod.available("ref", dtype):
+        pytest.skip("oracle/_ref not built")
+    from test_gpu_degenerate import degenerate_pairs
+    port, ref = oracle_mod.Oracle("port", dtype), oracle_mod.Oracle("ref", dtype)
+    a, b, _cat = degenerate_pairs(8000, nv, seed=3 + nv, dtype=dtype)
+    s1, d1 = port.gjk(a, b, nthreads=4)
+    s2, d2 = ref.gjk(a, b, nthreads=4)
+    assert np.array_equal(d1, d2, equal_nan=True) and live_simplex_equal(s1, s2)
+    a, b, _cat = degenerate_pairs(8000, nv, seed=3 + nv, dtype=dtype, large=1e3)
+    s1, d1 = port.gjk(a, b, nthreads=4)
+    s2, d2 = ref.gjk(a, b, nthreads=4)
+    e1, e2 = port.epa(a, b, s1, d1, nthreads=4), ref.epa(a, b, s2, d2, nthreads=4)
+    assert np.array_equal(e1[1], e2[1], equal_nan=True) and np.array_equal(e1[2], e2[2], equal_nan=True)
+    assert np.array_equal(e1[0]["witnesses"], e2[0]["witnesses"], equal_nan=True)
