@@ -659,9 +659,11 @@ epa_gate_kernel(const SimplexT<T>* __restrict__ simplices, const T* __restrict__
 }
 
 // Persistent EPA kernel: warps pull colliding pairs from the queue through an atomic ticket, so pairs whose
-// expansion needs 60 iterations do not hold up those that need 3.
+// expansion needs 60 iterations do not hold up those that need 3.  fp32: four 8-warp CTAs per SM (64 registers, 24
+// bytes of spills) instead of three at 80 registers -- config 3: 7.64 against 8.44 ms per Mi pairs; five CTAs at 48
+// registers lose again (9.2 ms).
 template <typename T, typename Source>
-__global__ void __launch_bounds__(EpaConfig<T>::kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(EpaConfig<T>::kWarpsPerBlock * 32, sizeof(T) == 4 ? 4 : 1)
 epa_queue_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
                  T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters) {
   __shared__ EpaWork<T> work[EpaConfig<T>::kWarpsPerBlock];
