@@ -281,6 +281,24 @@ def ours(args, workload):
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(pkg, nv, spread, a, b)
+            # second bound of SURVEY.md section 8(d): non-FMA fp32 lane-ops.  F_GJK = I*(2*V*5 + 150) + 100 per pair with
+            # I = the pairs' GJK iteration count, taken from the oracle on a sample of this very batch.
+            try:
+                om = load_oracle()
+                m = min(n, 1 << 15)
+                _s, _d, it = om.Oracle("port", np.float32).gjk(a[:m], b[:m], nthreads=host_threads(), want_iters=True)
+                mean_it = float(np.mean(it))
+                flops = mean_it * (2 * nv * 5 + 150) + 100
+                mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+                sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                fp_peak = sms * 128 * mhz * 1e6 / 1e12
+                fp_ach = flops * n / (gjk_ms * 1e-3) / 1e12
+                out["roofline_fp32"] = {"bound": "fp32 lane-ops, FMA off", "achieved": fp_ach, "peak": fp_peak,
+                                        "unit": "TFLOP/s", "frac": fp_ach / fp_peak, "flops_per_pair": flops,
+                                        "mean_gjk_iterations": mean_it,
+                                        "note": "looser than the HBM bound, which is therefore the roofline reported above"}
+            except Exception as e:  # noqa: BLE001
+                out["roofline_fp32"] = {"error": str(e)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
