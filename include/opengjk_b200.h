@@ -12,7 +12,11 @@
  *     calling thread is available from ogjk_last_error().  The reference checks no CUDA call at all.
  *   - launches go to the stream selected with ogjk_set_stream() (default: the legacy default stream the
  *     reference uses) and, like the reference (openGJK.cu:2983, 3003, 3141, 3161), each *_device call ends with a
- *     device synchronisation unless ogjk_set_sync(0) was called.
+ *     device synchronisation unless ogjk_set_sync(0) was called.  Asynchronous calls of one thread may be in flight
+ *     on several streams at once: the library's scratch (tickets, EPA queue, ...) is kept per (device, stream).
+ *   - device descriptor arrays returned by allocate_* are remembered so that *_device calls on them can take the
+ *     dense fast kernels; the remembered layout is re-validated against the live descriptors on the device at every
+ *     call, so editing or re-pointing descriptors after upload is allowed (it selects the general kernels).
  * Semantics kept from the reference: n <= 0 is a silent no-op; simplices[i] on input and bd.s / bd.s_idx are
  * ignored by GJK; EPA writes the penetration depth as a NEGATIVE distance and leaves pairs with
  * distance > epsilon untouched except for the contact normal.
@@ -44,6 +48,25 @@ int ogjk_set_device(int device);
 int ogjk_set_stream(void* stream);
 /* 1 (default): *_device calls synchronise the device before returning, as the reference does; 0: async. */
 int ogjk_set_sync(int enabled);
+/* Multi-GPU (the reference is single-device).  With more than one device selected, the
+ * host-pointer entry points (compute_minimum_distance, compute_collision_information[_witness], compute_gjk_epa and
+ * the three *_indexed host calls) split the pair range into one contiguous slice per device; a persistent host
+ * thread per device runs the single-device path on its slice and copies the results straight into the caller's
+ * arrays at the slice offset (indexed calls: the pool is replicated, the pair list sliced).  No collective, nothing
+ * exchanged.  devices == NULL selects ordinals 0..count-1; count <= 1 restores single-device behaviour.  The same
+ * selection can be made without touching the caller's code through the environment: OGJK_DEVICES=all | <count> |
+ * <i,j,...>.  Process-wide.  The *_device entry points always use the calling thread's current device. */
+int ogjk_set_devices(int count, const int* devices);
+/* Frees the device buffers the calling thread has cached (the host-pointer path keeps its staging buffers between
+ * calls instead of cudaMalloc/cudaFree per call as the reference does, openGJK.cu:2889-2954, 3034-3048; scratch of the
+ * EPA queue / broad phase / contact response).  No call of this thread may be in flight. */
+int ogjk_release_cached_buffers(void);
+/* Plain device-memory helpers so that a caller without the CUDA toolkit headers (the drop-in example.h) can follow
+ * the reference's allocate -> upload -> launch -> download -> free sequence (examples/gpu/example.cu:86-119). */
+int ogjk_device_malloc(size_t bytes, void** d_ptr); /* zero-filled */
+int ogjk_device_free(void* d_ptr);
+int ogjk_memcpy_to_device(void* d_dst, const void* src, size_t bytes);
+int ogjk_memcpy_from_device(void* dst, const void* d_src, size_t bytes);
 /* Number of kernels this library has launched on the calling thread since the last reset (bench accounting). */
 long long ogjk_launch_count(int reset);
 /* Uniform-grid broad phase on the device (the step before the hot path in the reference's caller:

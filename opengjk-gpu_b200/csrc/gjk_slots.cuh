@@ -6,9 +6,8 @@
 //     (xyz interleaved).  A finished thread takes the next pair index from a global ticket and refills its slot with
 //     two TMA bulk copies (cp.async.bulk global->shared, completion on the slot's own mbarrier); while the copy is
 //     in flight the other 31 lanes keep iterating.  This is the work queue that rebalances pairs whose iteration
-//     counts diverge (1..25 iterations, mean 3.8 at 64 vertices).  Tickets are drawn per warp in chunks of 64 (one
-//     atomic per ~8 warp iterations instead of one per iteration), and the chunk that will be needed
-//     `prefetch_ahead` pairs later is pulled into L2 with cp.async.bulk.prefetch so that refills hit L2, not HBM;
+//     counts diverge (1..25 iterations, mean 3.8 at 64 vertices).  Tickets are drawn per warp in chunks of 32 (one
+//     atomic per ~8 warp iterations instead of one per iteration);
 //   * slot stride is an odd multiple of 16 bytes, so the 128-bit shared loads of the 32 lanes of a warp (each in
 //     its own slot) are bank-conflict free;
 //   * the support scan walks the slot four vertices (three 128-bit loads) at a time with packed FMUL2 products and
@@ -59,9 +58,6 @@ OGJK_D void tma_bulk_load(uint32_t dst_smem, const void* src_gmem, uint32_t byte
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src_gmem), "r"(bytes), "r"(bar)
                : "memory");
-}
-OGJK_D void tma_prefetch_l2(const void* src_gmem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 OGJK_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -413,8 +409,8 @@ template <typename T, bool EQ>
 __global__ void __launch_bounds__(kSlotThreads)
 gjk_slots_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, int nv1, int nv2,
                  SimplexT<T>* __restrict__ simplices, T* __restrict__ distances, unsigned n,
-                 const uint16_t* __restrict__ utab_g, unsigned* __restrict__ ticket, unsigned prefetch_ahead,
-                 unsigned zero, const CollisionPair* __restrict__ pairs) {
+                 const uint16_t* __restrict__ utab_g, unsigned* __restrict__ ticket, unsigned zero,
+                 const CollisionPair* __restrict__ pairs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t sbytes = slot_bytes(nv1, nv2, (int)sizeof(T));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // one mbarrier per thread
@@ -441,7 +437,6 @@ gjk_slots_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, int
   TicketFeed feed;
   feed.init(ticket, pairs, n, lane);
   GjkState<T> g;
-  (void)prefetch_ahead;
 
   for (;;) {
     // ---- hand out work (two passes: a request may straddle two ticket chunks) --------------------------------------

@@ -11,8 +11,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/opengjk_b200.h"
@@ -187,30 +190,74 @@ void launch_uniform_instance(const T* c1, const T* c2, int nv1, int nv2, Simplex
   gjk_uniform_kernel<T, L, VPL><<<grid, block, 0, t_stream>>>(c1, c2, nv1, nv2, simp, dist, n, tabs);
 }
 
+// ---- per-(thread, device, stream) scratch ---------------------------------------------------------------------
+// The GJK ticket, the EPA counters + queue and the broad-phase / contact-response work buffers are written by the
+// kernels of one call and must not be shared by two calls in flight.  Calls on one stream are ordered by the stream;
+// calls issued asynchronously (ogjk_set_sync(0)) on DIFFERENT streams of one thread get different buffers because
+// the scratch is keyed by (device, stream).  Grow-only; released by ogjk_release_cached_buffers().
+struct Scratch {
+  int* ptr = nullptr;
+  size_t ints = 0;
+};
+struct StreamScratch {
+  int dev = -1;
+  cudaStream_t stream = nullptr;
+  unsigned* ticket = nullptr;
+  Scratch epa, bp, cr, flag;
+};
+thread_local std::vector<StreamScratch> t_sscratch;
+int stream_scratch(StreamScratch** out) {
+  int dev = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail_msg("device ordinal out of range");
+  for (StreamScratch& x : t_sscratch)
+    if (x.dev == dev && x.stream == t_stream) {
+      *out = &x;
+      return 0;
+    }
+  StreamScratch x;
+  x.dev = dev;
+  x.stream = t_stream;
+  t_sscratch.push_back(x);
+  *out = &t_sscratch.back();
+  return 0;
+}
+int scratch_grow(Scratch& sc, size_t ints, int** out) {
+  if (sc.ints < ints) {
+    if (sc.ptr) cudaFree(sc.ptr);
+    sc.ptr = nullptr;
+    sc.ints = 0;
+    OGJK_CK(cudaMalloc(&sc.ptr, ints * sizeof(int)));
+    sc.ints = ints;
+  }
+  *out = sc.ptr;
+  return 0;
+}
+int ticket_buffer(unsigned** out) {
+  StreamScratch* ss = nullptr;
+  if (int rc = stream_scratch(&ss)) return rc;
+  if (!ss->ticket) OGJK_CK(cudaMalloc(&ss->ticket, sizeof(unsigned)));
+  *out = ss->ticket;
+  return 0;
+}
+
 // ---- persistent slot kernel (fp32, both vertex sets of a pair fit one shared-memory slot) ----------------------
-thread_local unsigned* t_ticket[kMaxDevices] = {};
 
 // development override: OGJK_GJK_KERNEL=slots|slotsws|uniform|generic forces one kernel family (A/B measurements)
+// (re-read on every call: the parity tests switch it between calls; one getenv costs ~50 ns)
 int forced_kernel() {
   const char* e = getenv("OGJK_GJK_KERNEL");
   return !e ? 0 : !strcmp(e, "slots") ? 1 : !strcmp(e, "uniform") ? 2 : !strcmp(e, "generic") ? 3 :
          !strcmp(e, "slotsws") ? 4 : 0;
 }
-// development override: OGJK_SLOTS_PREFETCH=<pairs> sets the L2 prefetch distance of the slot kernel (0 = off)
-unsigned slots_prefetch_ahead() {
-  const char* e = getenv("OGJK_SLOTS_PREFETCH");
-  const long v = e ? atol(e) : 0;  // measured: no gain, +40 % DRAM reads (profiles/r1d_gjk_slots_v2.txt)
-  return v < 0 ? 0u : (unsigned)v;
-}
 
 template <typename T>
 int launch_gjk_slots(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist,
                      const CollisionPair* pairs = nullptr) {
-  int dev = 0;
-  OGJK_CK(cudaGetDevice(&dev));
   const uint16_t* utab = nullptr;
   if (int rc = device_unified_table(&utab)) return rc;
-  if (!t_ticket[dev]) OGJK_CK(cudaMalloc(&t_ticket[dev], sizeof(unsigned)));
+  unsigned* ticket = nullptr;
+  if (int rc = ticket_buffer(&ticket)) return rc;
   const size_t smem = (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2, (int)sizeof(T));
   // the interleaved scan needs ~40 more registers: only where shared memory, not registers, bounds occupancy
   auto kern = (sizeof(T) == 4 && nv1 == nv2 && nv1 >= 32) ? gjk_slots_kernel<T, true> : gjk_slots_kernel<T, false>;
@@ -218,9 +265,8 @@ int launch_gjk_slots(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT
   if (int rc = persistent_grid(kern, kSlotThreads, smem, &grid)) return rc;
   const long long need = ((long long)n + kSlotThreads - 1) / kSlotThreads;
   if (grid > need) grid = need;
-  OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
-  kern<<<(unsigned)grid, kSlotThreads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab, t_ticket[dev],
-                                                         slots_prefetch_ahead(), 0u, pairs);
+  OGJK_CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned), t_stream));
+  kern<<<(unsigned)grid, kSlotThreads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab, ticket, 0u, pairs);
   return finish_launch("gjk slots kernel");
 }
 
@@ -257,11 +303,10 @@ int ws_compute_warps(int nv1, int nv2, int esize) {
 template <typename T, int CW, int LP>
 int launch_gjk_slots_ws_cw(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist, T* nrm,
                            int* queue, int* count, const CollisionPair* pairs) {
-  int dev = 0;
-  OGJK_CK(cudaGetDevice(&dev));
   const uint16_t* utab = nullptr;
   if (int rc = device_unified_table(&utab)) return rc;
-  if (!t_ticket[dev]) OGJK_CK(cudaMalloc(&t_ticket[dev], sizeof(unsigned)));
+  unsigned* ticket = nullptr;
+  if (int rc = ticket_buffer(&ticket)) return rc;
   constexpr int nslots = CW * 32 / LP;
   constexpr int es = (int)sizeof(T);
   const size_t smem = (size_t)ws_fixed_bytes(nslots, es) + kSlotPadBytes + (size_t)nslots * ws_slot_layout(nv1, nv2, LP, es).stride;
@@ -274,8 +319,8 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const T* c1, int nv2, const T* c2, Si
   if (int rc = persistent_grid(kern, threads, smem, &grid)) return rc;
   const long long need = ((long long)n + nslots - 1) / nslots;
   if (grid > need) grid = need;
-  OGJK_CK(cudaMemsetAsync(t_ticket[dev], 0, sizeof(unsigned), t_stream));
-  kern<<<(unsigned)grid, threads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab, t_ticket[dev], 0u,
+  OGJK_CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned), t_stream));
+  kern<<<(unsigned)grid, threads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab, ticket, 0u,
                                                     nrm, queue, count, pairs, ws_dense_chunk());
   return finish_launch("gjk slots (warp-specialised) kernel");
 }
@@ -347,27 +392,11 @@ int launch_gjk_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, Simple
   return finish_launch("gjk uniform kernel");
 }
 
-// ---- per-thread, per-device scratch for the EPA work queue (grow-only) --------------------------------------
-struct Scratch {
-  int* ptr = nullptr;
-  size_t ints = 0;
-};
-thread_local Scratch t_scratch[kMaxDevices];
-
+// ---- scratch for the EPA work queue ------------------------------------------------------------------------------
 int epa_scratch(size_t ints, int** out) {
-  int dev = 0;
-  OGJK_CK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= kMaxDevices) return fail_msg("device ordinal out of range");
-  Scratch& s = t_scratch[dev];
-  if (s.ints < ints) {
-    if (s.ptr) cudaFree(s.ptr);
-    s.ptr = nullptr;
-    s.ints = 0;
-    OGJK_CK(cudaMalloc(&s.ptr, ints * sizeof(int)));
-    s.ints = ints;
-  }
-  *out = s.ptr;
-  return 0;
+  StreamScratch* ss = nullptr;
+  if (int rc = stream_scratch(&ss)) return rc;
+  return scratch_grow(ss->epa, ints, out);
 }
 
 template <typename T, int G, typename Source>
@@ -504,7 +533,13 @@ std::mutex g_pool_mutex;
 std::vector<std::pair<const void*, PoolInfo>> g_pools;  // keyed by the device descriptor pointer
 void register_pool(const void* d_desc, const void* d_coords, int nv, int count, int max_nv = 0) {
   std::lock_guard<std::mutex> lock(g_pool_mutex);
-  g_pools.push_back({d_desc, PoolInfo{d_coords, nv, count, max_nv > 0 ? max_nv : nv}});
+  const PoolInfo info{d_coords, nv, count, max_nv > 0 ? max_nv : nv};
+  for (auto& p : g_pools)
+    if (p.first == d_desc) {  // a recycled address (the caller cudaFree'd a registered array): the new entry wins
+      p.second = info;
+      return;
+    }
+  g_pools.push_back({d_desc, info});
 }
 void unregister_pool(const void* d_desc) {
   std::lock_guard<std::mutex> lock(g_pool_mutex);
@@ -522,6 +557,30 @@ bool lookup_pool(const void* d_desc, PoolInfo* out) {
       return true;
     }
   return false;
+}
+
+// The registry is only a hint: before a fast kernel reads the remembered layout, the live descriptors are checked
+// against it on the device (one pass over `count` descriptors, a 4-byte read-back).  *ok = false sends the call to
+// the descriptor-reading general kernels, so a caller that edits d_bd[i].coord / numpoints after upload, or re-uses
+// a freed address without telling the library, still gets results for the descriptors it passed.
+template <typename T>
+int pool_layout_holds(const void* d_desc, const PoolInfo& info, int count, bool* ok) {
+  *ok = false;
+  if (info.nv <= 0 || count > info.count) return 0;
+  StreamScratch* ss = nullptr;
+  if (int rc = stream_scratch(&ss)) return rc;
+  int* flag = nullptr;
+  if (int rc = scratch_grow(ss->flag, 1, &flag)) return rc;
+  OGJK_CK(cudaMemsetAsync(flag, 0, sizeof(int), t_stream));
+  validate_dense_kernel<T><<<(unsigned)((count + 255) / 256), 256, 0, t_stream>>>((const PolytopeT<T>*)d_desc, count,
+                                                                                 (const T*)info.coords, info.nv, flag);
+  ++t_launches;
+  OGJK_CK(cudaGetLastError());
+  int h = 1;
+  OGJK_CK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, t_stream));
+  OGJK_CK(cudaStreamSynchronize(t_stream));
+  *ok = h == 0;
+  return 0;
 }
 
 // GJK (and optionally the fused EPA gate + EPA) over `pairs` into a uniform fp32 pool.  Returns 1 when the batch does
@@ -774,30 +833,43 @@ int run_pairs_host_dense(int n, const PolytopeT<T>* bd1, const PolytopeT<T>* bd2
   if (stages & kEpa)
     if (int rc = pool_get(P, kSlotNrm, (size_t)n * 3 * sizeof(T), (void**)&d_nrm)) return rc;
 
+  // Chunks are sized in PAIRS: at least 65536, so that every chunk is large enough for the persistent slot kernels
+  // (>= 32768 pairs, ~3.5 waves of 148 CTAs x 128 slots) -- the host-pointer API then runs the same kernels as the
+  // device-resident path -- and at least ~24 MB of coordinates, so that small polytopes still move in large DMAs.
   const size_t pair_bytes = (size_t)(nv1 + nv2) * 3 * sizeof(T);
-  size_t chunk_pairs = (size_t)(24u << 20) / pair_bytes;  // ~24 MB of coordinates per chunk
-  if (chunk_pairs < 8192) chunk_pairs = 8192;
+  size_t chunk_pairs = (size_t)(24u << 20) / pair_bytes;
+  if (chunk_pairs < 65536) chunk_pairs = 65536;
   const size_t chunks = ((size_t)n + chunk_pairs - 1) / chunk_pairs;
+  chunk_pairs = (((size_t)n + chunks - 1) / chunks + 255) & ~(size_t)255;  // equal chunks: no undersized tail
   if (int rc = pool_streams(P, chunks)) return rc;
+  // EPA-only calls overwrite their inputs (simplices, distances): there the whole descriptor array is validated before
+  // anything is queued, so that a batch that turns out not to be dense is handed to the general path untouched.  For
+  // calls that start with GJK the outputs are pure outputs, and validation runs chunk by chunk behind the transfers.
+  if (!(stages & kGjk) && (!dense_uniform_range(bd1, 0, (size_t)n) || !dense_uniform_range(bd2, 0, (size_t)n))) return 1;
   // order the pool's streams after whatever the caller queued on the selected stream
   OGJK_CK(cudaEventRecord(P.ev_done[0], t_stream));
   OGJK_CK(cudaStreamWaitEvent(P.s_copy, P.ev_done[0], 0));
   OGJK_CK(cudaStreamWaitEvent(P.s_comp, P.ev_done[0], 0));
   OGJK_CK(cudaStreamWaitEvent(P.s_out, P.ev_done[0], 0));
+  // every exit below -- error or not -- leaves no copy to or from the caller's arrays in flight
+  struct Drain {
+    DevicePool& p;
+    ~Drain() {
+      cudaStreamSynchronize(p.s_copy);
+      cudaStreamSynchronize(p.s_comp);
+      cudaStreamSynchronize(p.s_out);
+    }
+  } drain{P};
 
   const T* h_c1 = bd1[0].coord;
   const T* h_c2 = bd2[0].coord;
   SyncOverride nosync;
   for (size_t k = 0; k < chunks; ++k) {
     const size_t lo = k * chunk_pairs;
+    if (lo >= (size_t)n) break;
     const int m = (int)(((size_t)n - lo) < chunk_pairs ? ((size_t)n - lo) : chunk_pairs);
-    if (!dense_uniform_range(bd1, lo, lo + m) || !dense_uniform_range(bd2, lo, lo + m)) {
-      // not a dense batch after all: drain what was queued and let the general path redo the whole call
-      cudaStreamSynchronize(P.s_copy);
-      cudaStreamSynchronize(P.s_comp);
-      cudaStreamSynchronize(P.s_out);
-      return 1;
-    }
+    if ((stages & kGjk) && (!dense_uniform_range(bd1, lo, lo + m) || !dense_uniform_range(bd2, lo, lo + m)))
+      return 1;  // not a dense batch after all: the general path redoes the whole call (queued work is drained)
     OGJK_CK(cudaMemcpyAsync(d_c1 + lo * nv1 * 3, h_c1 + lo * nv1 * 3, (size_t)m * nv1 * 3 * sizeof(T),
                             cudaMemcpyHostToDevice, P.s_copy));
     OGJK_CK(cudaMemcpyAsync(d_c2 + lo * nv2 * 3, h_c2 + lo * nv2 * 3, (size_t)m * nv2 * 3 * sizeof(T),
@@ -971,9 +1043,153 @@ int run_indexed_host(int num_polytopes, int num_pairs, const PolytopeT<T>* polyt
   return rc;
 }
 
-// ---- broad phase (SURVEY section 8(f) row 1; reference visualization/integrate_final_gjk.cu:916-1002) -------------
-thread_local Scratch t_bp_scratch[kMaxDevices];
+// ---- multi-GPU fan-out of the host-pointer calls -------------------------------------------
+// The reference's API has no device argument and uses the current device.  When more than one device is selected
+// (ogjk_set_devices(), or OGJK_DEVICES=all|<count>|<i,j,...> in the environment) the host-pointer entry points split
+// the pair range into one contiguous slice per device: a persistent host thread per device runs the single-device
+// path on its slice -- own streams, own cached device buffers, chunked H2D / kernels / D2H overlapped as above -- and
+// writes straight into the caller's arrays at the slice offset.  Pairs are independent, so nothing is exchanged;
+// for the indexed calls the polytope pool is uploaded to every device and only the pair list is sliced.
+class DeviceWorker {
+ public:
+  explicit DeviceWorker(int dev) : dev_(dev), th_([this] { loop(); }) {}
+  void submit(std::function<int()> job) {
+    std::lock_guard<std::mutex> lk(m_);
+    job_ = std::move(job);
+    state_ = 1;
+    cv_.notify_all();
+  }
+  int wait(std::string* err) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&] { return state_ == 2; });
+    state_ = 0;
+    *err = err_;
+    return rc_;
+  }
 
+ private:
+  void loop() {
+    const cudaError_t e = cudaSetDevice(dev_);
+    for (;;) {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_.wait(lk, [&] { return state_ == 1; });
+      std::function<int()> job = std::move(job_);
+      lk.unlock();
+      int rc = e == cudaSuccess ? job() : fail("cudaSetDevice", e);
+      const std::string msg = rc ? t_err : std::string();
+      lk.lock();
+      rc_ = rc;
+      err_ = msg;
+      state_ = 2;
+      cv_.notify_all();
+    }
+  }
+  int dev_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::function<int()> job_;
+  int state_ = 0;  // 0 idle, 1 job posted, 2 result ready
+  int rc_ = 0;
+  std::string err_;
+  std::thread th_;  // last member: starts after the others are constructed; never joined (workers live to exit)
+};
+
+std::mutex g_dev_mutex;
+std::vector<int> g_devices;       // selected devices; empty or one entry = single-device behaviour
+bool g_devices_from_env = false;  // environment consulted
+DeviceWorker* g_workers[kMaxDevices] = {};
+
+std::vector<int> selected_devices() {
+  std::lock_guard<std::mutex> lk(g_dev_mutex);
+  if (!g_devices_from_env) {
+    g_devices_from_env = true;
+    const char* e = getenv("OGJK_DEVICES");
+    if (e && *e && g_devices.empty()) {
+      int count = 0;
+      cudaGetDeviceCount(&count);
+      if (!strcmp(e, "all")) {
+        for (int i = 0; i < count; ++i) g_devices.push_back(i);
+      } else if (strchr(e, ',')) {
+        for (const char* q = e; *q;) {
+          const int d = atoi(q);
+          if (d >= 0 && d < count) g_devices.push_back(d);
+          q = strchr(q, ',');
+          if (!q) break;
+          ++q;
+        }
+      } else {
+        const int want = atoi(e);
+        for (int i = 0; i < want && i < count; ++i) g_devices.push_back(i);
+      }
+    }
+  }
+  return g_devices;
+}
+
+// runs part(g, G) for g in [0, G) on the workers of `devs`; first failure wins
+int fan_out(const std::vector<int>& devs, const std::function<int(int, int)>& part) {
+  const int G = (int)devs.size();
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mutex);
+    for (int d : devs)
+      if (!g_workers[d]) g_workers[d] = new DeviceWorker(d);
+  }
+  // one fan-out at a time per process: the workers (and their cached buffers) are shared
+  static std::mutex fan_mutex;
+  std::lock_guard<std::mutex> fan(fan_mutex);
+  for (int g = 0; g < G; ++g) g_workers[devs[g]]->submit([=] { return part(g, G); });
+  int rc = 0;
+  std::string first;
+  for (int g = 0; g < G; ++g) {
+    std::string msg;
+    const int r = g_workers[devs[g]]->wait(&msg);
+    if (r && !rc) {
+      rc = r;
+      first = "device " + std::to_string(devs[g]) + ": " + msg;
+    }
+  }
+  if (rc) t_err = first;
+  return rc;
+}
+
+constexpr long long kMinPairsPerDevice = 65536;  // below this a second device costs more than it saves
+
+template <typename T>
+int run_pairs_host_multi(int n, const PolytopeT<T>* bd1, const PolytopeT<T>* bd2, SimplexT<T>* simplices, T* distances,
+                         T* normals, T* witness1, T* witness2, int stages) {
+  std::vector<int> devs = selected_devices();
+  if (n > 0 && devs.size() > 1) {
+    const long long fit = (long long)n / kMinPairsPerDevice;
+    if (fit < (long long)devs.size()) devs.resize(fit < 1 ? 1 : (size_t)fit);
+  }
+  if (devs.size() <= 1 || n <= 0 || !bd1 || !bd2 || !simplices || !distances)
+    return run_pairs_host<T>(n, bd1, bd2, simplices, distances, normals, witness1, witness2, stages);
+  return fan_out(devs, [=](int g, int G) {
+    const long long lo = (long long)n * g / G, hi = (long long)n * (g + 1) / G;
+    return run_pairs_host<T>((int)(hi - lo), bd1 + lo, bd2 + lo, simplices + lo, distances + lo,
+                             normals ? normals + 3 * lo : nullptr, witness1 ? witness1 + 3 * lo : nullptr,
+                             witness2 ? witness2 + 3 * lo : nullptr, stages);
+  });
+}
+
+template <typename T>
+int run_indexed_host_multi(int num_polytopes, int num_pairs, const PolytopeT<T>* polytopes, const CollisionPair* pairs,
+                           SimplexT<T>* simplices, T* distances, T* normals, int stages) {
+  std::vector<int> devs = selected_devices();
+  if (num_pairs > 0 && devs.size() > 1) {
+    const long long fit = (long long)num_pairs / kMinPairsPerDevice;
+    if (fit < (long long)devs.size()) devs.resize(fit < 1 ? 1 : (size_t)fit);
+  }
+  if (devs.size() <= 1 || num_pairs <= 0 || num_polytopes <= 0 || !polytopes || !pairs || !simplices || !distances)
+    return run_indexed_host<T>(num_polytopes, num_pairs, polytopes, pairs, simplices, distances, normals, stages);
+  return fan_out(devs, [=](int g, int G) {
+    const long long lo = (long long)num_pairs * g / G, hi = (long long)num_pairs * (g + 1) / G;
+    return run_indexed_host<T>(num_polytopes, (int)(hi - lo), polytopes, pairs + lo, simplices + lo, distances + lo,
+                               normals ? normals + 3 * lo : nullptr, stages);
+  });
+}
+
+// ---- broad phase (SURVEY section 8(f) row 1; reference visualization/integrate_final_gjk.cu:916-1002) -------------
 int broadphase_pairs(int n, const float4* d_pos, float cell_size, float boundary, int grid_size, CollisionPair* d_pairs,
                      int max_pairs, long long* num_pairs) {
   if (num_pairs) *num_pairs = 0;
@@ -981,20 +1197,12 @@ int broadphase_pairs(int n, const float4* d_pos, float cell_size, float boundary
   if (!d_pos || (!d_pairs && max_pairs > 0)) return fail_msg("null argument");
   if (!(cell_size > 0.0f) || grid_size < 1 || grid_size > 512) return fail_msg("bad grid (cell_size > 0, 1 <= grid_size <= 512)");
   const size_t cells = (size_t)grid_size * grid_size * grid_size;
-  int dev = 0;
-  OGJK_CK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= kMaxDevices) return fail_msg("device ordinal out of range");
   // obj_cell[n] | cell_count[cells] | cursor[cells] | cell_start[cells + 1] | cell_objs[n] | pair_counts[n] | pair_offsets[n + 1]
   const size_t ints = 3 * (size_t)n + 3 * cells + (size_t)n + 2;
-  Scratch& sc = t_bp_scratch[dev];
-  if (sc.ints < ints) {
-    if (sc.ptr) cudaFree(sc.ptr);
-    sc.ptr = nullptr;
-    sc.ints = 0;
-    OGJK_CK(cudaMalloc(&sc.ptr, ints * sizeof(int)));
-    sc.ints = ints;
-  }
-  int* obj_cell = sc.ptr;
+  StreamScratch* ss = nullptr;
+  if (int rc = stream_scratch(&ss)) return rc;
+  int* obj_cell = nullptr;
+  if (int rc = scratch_grow(ss->bp, ints, &obj_cell)) return rc;
   int* cell_count = obj_cell + n;
   int* cursor = cell_count + cells;
   int* cell_start = cursor + cells;
@@ -1025,8 +1233,6 @@ int broadphase_pairs(int n, const float4* d_pos, float cell_size, float boundary
 }
 
 // ---- contact response (reference visualization/integrate_final_gjk.cu:572-689, 1039-1054) ---
-thread_local Scratch t_cr_scratch[kMaxDevices];
-
 template <typename T>
 int contact_response(int num_pairs, const CollisionPair* d_pairs, const T* d_dist, const SimplexT<T>* d_simp,
                      const T* d_nrm, const int* d_sub_mesh_body, int num_objects, float4* d_pos, const float4* d_vel_ping,
@@ -1039,9 +1245,6 @@ int contact_response(int num_pairs, const CollisionPair* d_pairs, const T* d_dis
   if (num_pairs > 0 && (!d_pairs || !d_dist || !d_simp || !d_nrm)) return fail_msg("null argument");
   if (d_vel_ping == d_vel_pong || d_ang_ping == d_ang_pong) return fail_msg("ping and pong buffers must differ");
   if (num_pairs > (1 << 30)) return fail_msg("too many pairs");
-  int dev = 0;
-  OGJK_CK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= kMaxDevices) return fail_msg("device ordinal out of range");
   const size_t slots = 2 * (size_t)num_pairs;
   int key_bits = 1;
   while ((1ll << key_bits) <= (long long)num_objects) ++key_bits;  // the sentinel key is num_objects itself
@@ -1053,17 +1256,12 @@ int contact_response(int num_pairs, const CollisionPair* d_pairs, const T* d_dis
   // counts[num_objects + 1] | seg_start[num_objects + 2] | keys[slots] x 2 | slot ids[slots] x 2 | positions_out | sort temp
   const size_t head = 2 * (size_t)num_objects + 4;
   const size_t ints = head + 4 * slots + 4 * (size_t)num_objects + (sort_bytes + 3) / 4 + 8;
-  Scratch& sc = t_cr_scratch[dev];
-  if (sc.ints < ints) {
-    if (sc.ptr) cudaFree(sc.ptr);
-    sc.ptr = nullptr;
-    sc.ints = 0;
-    OGJK_CK(cudaMalloc(&sc.ptr, ints * sizeof(int)));
-    sc.ints = ints;
-  }
-  int* counts = sc.ptr;
+  StreamScratch* ss = nullptr;
+  if (int rc = stream_scratch(&ss)) return rc;
+  int* counts = nullptr;
+  if (int rc = scratch_grow(ss->cr, ints, &counts)) return rc;
   int* seg_start = counts + num_objects + 1;
-  unsigned* keys_in = (unsigned*)(sc.ptr + ((head + 3) & ~(size_t)3));
+  unsigned* keys_in = (unsigned*)(counts + ((head + 3) & ~(size_t)3));
   unsigned* keys_out = keys_in + slots;
   unsigned* slots_in = keys_out + slots;
   unsigned* slots_out = slots_in + slots;
@@ -1152,6 +1350,75 @@ int ogjk_broadphase_pairs_device(int num_objects, const float* d_pos_radius, flo
   return broadphase_pairs(num_objects, (const float4*)d_pos_radius, cell_size, boundary, grid_size,
                           (CollisionPair*)d_pairs, max_pairs, num_pairs);
 }
+int ogjk_set_devices(int count, const int* devices) {
+  int have = 0;
+  OGJK_CK(cudaGetDeviceCount(&have));
+  std::vector<int> v;
+  for (int i = 0; i < count; ++i) {
+    const int d = devices ? devices[i] : i;
+    if (d < 0 || d >= have || d >= kMaxDevices) return fail_msg("ogjk_set_devices: device ordinal out of range");
+    for (int x : v)
+      if (x == d) return fail_msg("ogjk_set_devices: device listed twice");
+    v.push_back(d);
+  }
+  std::lock_guard<std::mutex> lk(g_dev_mutex);
+  g_devices = v;
+  g_devices_from_env = true;  // an explicit selection overrides OGJK_DEVICES
+  return 0;
+}
+int ogjk_release_cached_buffers(void) {
+  // buffers cached by the calling thread on every device: host-path staging pools + scratch (kernels must be idle)
+  int cur = 0;
+  OGJK_CK(cudaGetDevice(&cur));
+  for (int d = 0; d < kMaxDevices; ++d) {
+    DevicePool& p = t_pool[d];
+    bool any = false;
+    for (int k = 0; k < kSlotCount; ++k) any = any || p.ptr[k];
+    if (!any) continue;
+    OGJK_CK(cudaSetDevice(d));
+    for (int k = 0; k < kSlotCount; ++k) {
+      cudaFree(p.ptr[k]);
+      p.ptr[k] = nullptr;
+      p.cap[k] = 0;
+    }
+  }
+  for (StreamScratch& x : t_sscratch) {
+    OGJK_CK(cudaSetDevice(x.dev));
+    cudaFree(x.ticket);
+    x.ticket = nullptr;
+    for (Scratch* sc : {&x.epa, &x.bp, &x.cr, &x.flag}) {
+      cudaFree(sc->ptr);
+      sc->ptr = nullptr;
+      sc->ints = 0;
+    }
+  }
+  OGJK_CK(cudaSetDevice(cur));
+  return 0;
+}
+int ogjk_device_malloc(size_t bytes, void** d_ptr) {
+  if (!d_ptr) return fail_msg("null argument");
+  *d_ptr = nullptr;
+  if (bytes == 0) return 0;
+  OGJK_CK(cudaMalloc(d_ptr, bytes));
+  OGJK_CK(cudaMemsetAsync(*d_ptr, 0, bytes, t_stream));  // zero-filled: results that EPA leaves unwritten are defined
+  return 0;
+}
+int ogjk_device_free(void* d_ptr) {
+  cudaFree(d_ptr);
+  return 0;
+}
+int ogjk_memcpy_to_device(void* d_dst, const void* src, size_t bytes) {
+  if (bytes == 0) return 0;
+  OGJK_CK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, t_stream));
+  OGJK_CK(cudaStreamSynchronize(t_stream));
+  return 0;
+}
+int ogjk_memcpy_from_device(void* dst, const void* d_src, size_t bytes) {
+  if (bytes == 0) return 0;
+  OGJK_CK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, t_stream));
+  OGJK_CK(cudaStreamSynchronize(t_stream));
+  return 0;
+}
 long long ogjk_launch_count(int reset) {
   const long long v = t_launches;
   if (reset) t_launches = 0;
@@ -1160,24 +1427,24 @@ long long ogjk_launch_count(int reset) {
 
 #define OGJK_DEFINE_API(P, REAL)                                                                                       \
   int ogjk_##P##_compute_minimum_distance(int n, const void* bd1, const void* bd2, void* simplices, REAL* distances) { \
-    return run_pairs_host<REAL>(n, (const PolytopeT<REAL>*)bd1, (const PolytopeT<REAL>*)bd2,                           \
+    return run_pairs_host_multi<REAL>(n, (const PolytopeT<REAL>*)bd1, (const PolytopeT<REAL>*)bd2,                           \
                                 (SimplexT<REAL>*)simplices, distances, nullptr, nullptr, nullptr, kGjk);               \
   }                                                                                                                    \
   int ogjk_##P##_compute_collision_information(int n, const void* bd1, const void* bd2, void* simplices,              \
                                                REAL* distances, REAL* contact_normals) {                              \
-    return run_pairs_host<REAL>(n, (const PolytopeT<REAL>*)bd1, (const PolytopeT<REAL>*)bd2,                           \
+    return run_pairs_host_multi<REAL>(n, (const PolytopeT<REAL>*)bd1, (const PolytopeT<REAL>*)bd2,                           \
                                 (SimplexT<REAL>*)simplices, distances, contact_normals, nullptr, nullptr, kEpa);       \
   }                                                                                                                    \
   int ogjk_##P##_compute_gjk_epa(int n, const void* bd1, const void* bd2, void* simplices, REAL* distances,            \
                                  REAL* contact_normals) {                                                              \
-    return run_pairs_host<REAL>(n, (const PolytopeT<REAL>*)bd1, (const PolytopeT<REAL>*)bd2,                           \
+    return run_pairs_host_multi<REAL>(n, (const PolytopeT<REAL>*)bd1, (const PolytopeT<REAL>*)bd2,                           \
                                 (SimplexT<REAL>*)simplices, distances, contact_normals, nullptr, nullptr,              \
                                 kGjk | kEpa);                                                                          \
   }                                                                                                                    \
   int ogjk_##P##_compute_collision_information_witness(int n, const void* bd1, const void* bd2, void* simplices,      \
                                                        REAL* distances, REAL* witness1, REAL* witness2,               \
                                                        REAL* contact_normals) {                                       \
-    return run_pairs_host<REAL>(n, (const PolytopeT<REAL>*)bd1, (const PolytopeT<REAL>*)bd2,                           \
+    return run_pairs_host_multi<REAL>(n, (const PolytopeT<REAL>*)bd1, (const PolytopeT<REAL>*)bd2,                           \
                                 (SimplexT<REAL>*)simplices, distances, contact_normals, witness1, witness2,            \
                                 kGjk | kEpa);                                                                          \
   }                                                                                                                    \
@@ -1195,13 +1462,24 @@ long long ogjk_launch_count(int reset) {
     *d_bd2 = f2.d_desc;                                                                                                \
     *d_coord1 = f1.d_coord;                                                                                            \
     *d_coord2 = f2.d_coord;                                                                                            \
-    /* remembered so that the *_device calls on these arrays can take the dense fast kernels (and skip the peek) */   \
+    cudaError_t e_ = cudaMalloc(d_simplices, (size_t)n * sizeof(SimplexT<REAL>));                                      \
+    if (e_ == cudaSuccess) {                                                                                           \
+      e_ = cudaMalloc((void**)d_distances, (size_t)n * sizeof(REAL));                                                  \
+      if (e_ != cudaSuccess) cudaFree(*d_simplices);                                                                   \
+    }                                                                                                                  \
+    if (e_ == cudaSuccess) e_ = cudaMemsetAsync(*d_simplices, 0, (size_t)n * sizeof(SimplexT<REAL>), t_stream);        \
+    if (e_ == cudaSuccess) e_ = cudaStreamSynchronize(t_stream);                                                       \
+    if (e_ != cudaSuccess) {                                                                                           \
+      release(f1);                                                                                                     \
+      release(f2);                                                                                                     \
+      *d_bd1 = *d_bd2 = *d_simplices = nullptr;                                                                        \
+      *d_coord1 = *d_coord2 = *d_distances = nullptr;                                                                  \
+      return fail("allocate_and_copy_device_arrays", e_);                                                              \
+    }                                                                                                                  \
+    /* remembered (after the last allocation succeeded) so that the *_device calls on these arrays can take the    */ \
+    /* dense fast kernels; the layout is re-validated on the device at every use (pool_layout_holds)               */ \
     register_pool(f1.d_desc, f1.d_coord, f1.uniform_nv, n, (int)f1.max_nv);                                            \
     register_pool(f2.d_desc, f2.d_coord, f2.uniform_nv, n, (int)f2.max_nv);                                            \
-    OGJK_CK(cudaMalloc(d_simplices, (size_t)n * sizeof(SimplexT<REAL>)));                                              \
-    OGJK_CK(cudaMalloc((void**)d_distances, (size_t)n * sizeof(REAL)));                                                \
-    OGJK_CK(cudaMemsetAsync(*d_simplices, 0, (size_t)n * sizeof(SimplexT<REAL>), t_stream));                           \
-    OGJK_CK(cudaStreamSynchronize(t_stream));                                                                          \
     return 0;                                                                                                          \
   }                                                                                                                    \
   int ogjk_##P##_compute_minimum_distance_device(int n, const void* d_bd1, const void* d_bd2, void* d_simplices,      \
@@ -1211,9 +1489,15 @@ long long ogjk_launch_count(int reset) {
     PoolInfo p1, p2;                                                                                                   \
     const bool known = lookup_pool(d_bd1, &p1) && lookup_pool(d_bd2, &p2) && p1.count >= n && p2.count >= n;           \
     if (known && p1.nv > 0 && p2.nv > 0) { /* arrays uploaded by allocate_and_copy_device_arrays, uniform + dense */   \
-      const int fast = launch_gjk_uniform<REAL>(n, p1.nv, (const REAL*)p1.coords, p2.nv, (const REAL*)p2.coords,       \
-                                                (SimplexT<REAL>*)d_simplices, d_distances);                            \
-      if (fast <= 0) return fast;                                                                                      \
+      bool ok1 = false, ok2 = false;                                                                                   \
+      if (int rc = pool_layout_holds<REAL>(d_bd1, p1, n, &ok1)) return rc;                                             \
+      if (ok1)                                                                                                         \
+        if (int rc = pool_layout_holds<REAL>(d_bd2, p2, n, &ok2)) return rc;                                           \
+      if (ok1 && ok2) {                                                                                                \
+        const int fast = launch_gjk_uniform<REAL>(n, p1.nv, (const REAL*)p1.coords, p2.nv, (const REAL*)p2.coords,     \
+                                                  (SimplexT<REAL>*)d_simplices, d_distances);                          \
+        if (fast <= 0) return fast;                                                                                    \
+      }                                                                                                                \
     }                                                                                                                  \
     if (known) nv = p1.max_nv;                                                                                         \
     else if (int rc = peek_numpoints<REAL>((const PolytopeT<REAL>*)d_bd1, &nv)) return rc;                             \
@@ -1308,7 +1592,7 @@ long long ogjk_launch_count(int reset) {
   }                                                                                                                    \
   int ogjk_##P##_compute_minimum_distance_indexed(int num_polytopes, int num_pairs, const void* polytopes,            \
                                                   const void* pairs, void* simplices, REAL* distances) {              \
-    return run_indexed_host<REAL>(num_polytopes, num_pairs, (const PolytopeT<REAL>*)polytopes,                         \
+    return run_indexed_host_multi<REAL>(num_polytopes, num_pairs, (const PolytopeT<REAL>*)polytopes,                         \
                                   (const CollisionPair*)pairs, (SimplexT<REAL>*)simplices, distances, nullptr, kGjk);  \
   }                                                                                                                    \
   int ogjk_##P##_compute_minimum_distance_indexed_device(int num_pairs, const void* d_polytopes,                      \
@@ -1316,11 +1600,15 @@ long long ogjk_launch_count(int reset) {
                                                          REAL* d_distances) {                                         \
     if (num_pairs <= 0) return 0;                                                                                      \
     PoolInfo info;                                                                                                     \
-    if (lookup_pool(d_polytopes, &info)) {                                                                             \
-      const int fast = launch_indexed_uniform<REAL>(num_pairs, info, (const CollisionPair*)d_pairs,                    \
-                                                    (const PolytopeT<REAL>*)d_polytopes, (SimplexT<REAL>*)d_simplices, \
-                                                    d_distances, nullptr, kGjkStage);                                  \
-      if (fast <= 0) return fast;                                                                                      \
+    if (num_pairs >= 32768 && lookup_pool(d_polytopes, &info)) {                                                       \
+      bool ok = false;                                                                                                 \
+      if (int rc = pool_layout_holds<REAL>(d_polytopes, info, info.count, &ok)) return rc;                             \
+      if (ok) {                                                                                                        \
+        const int fast = launch_indexed_uniform<REAL>(num_pairs, info, (const CollisionPair*)d_pairs,                  \
+                                                      (const PolytopeT<REAL>*)d_polytopes,                             \
+                                                      (SimplexT<REAL>*)d_simplices, d_distances, nullptr, kGjkStage);  \
+        if (fast <= 0) return fast;                                                                                    \
+      }                                                                                                                \
     }                                                                                                                  \
     int nv = 0;                                                                                                        \
     if (int rc = peek_numpoints<REAL>((const PolytopeT<REAL>*)d_polytopes, &nv)) return rc;                            \
@@ -1336,7 +1624,7 @@ long long ogjk_launch_count(int reset) {
   int ogjk_##P##_compute_epa_indexed(int num_polytopes, int num_pairs, const void* polytopes, const void* pairs,      \
                                      void* simplices, REAL* distances, REAL* contact_normals) {                       \
     if (num_pairs <= 0) return 0;                                                                                      \
-    return run_indexed_host<REAL>(num_polytopes, num_pairs, (const PolytopeT<REAL>*)polytopes,                         \
+    return run_indexed_host_multi<REAL>(num_polytopes, num_pairs, (const PolytopeT<REAL>*)polytopes,                         \
                                   (const CollisionPair*)pairs, (SimplexT<REAL>*)simplices, distances,                  \
                                   contact_normals, kEpa);                                                              \
   }                                                                                                                    \
@@ -1344,7 +1632,7 @@ long long ogjk_launch_count(int reset) {
                                          const void* pairs, void* simplices, REAL* distances,                         \
                                          REAL* contact_normals) {                                                     \
     if (num_pairs <= 0) return 0;                                                                                      \
-    return run_indexed_host<REAL>(num_polytopes, num_pairs, (const PolytopeT<REAL>*)polytopes,                         \
+    return run_indexed_host_multi<REAL>(num_polytopes, num_pairs, (const PolytopeT<REAL>*)polytopes,                         \
                                   (const CollisionPair*)pairs, (SimplexT<REAL>*)simplices, distances,                  \
                                   contact_normals, kGjk | kEpa);                                                       \
   }                                                                                                                    \

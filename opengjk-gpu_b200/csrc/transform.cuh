@@ -75,4 +75,17 @@ init_polytopes_kernel(PolytopeT<T>* __restrict__ polytopes, T* __restrict__ vert
   polytopes[sm] = p;
 }
 
+// Do the first n descriptors still describe the dense uniform layout the library remembers for this array
+// (numpoints == nv, coord == base + i * nv * 3)?  Descriptor arrays are plain device memory that the caller may edit
+// or re-point after upload (the reference allows it); the fast kernels read the remembered layout, so every call
+// re-checks it and falls back to the descriptor-reading kernels when it no longer holds.
+template <typename T>
+__global__ void __launch_bounds__(256)
+validate_dense_kernel(const PolytopeT<T>* __restrict__ desc, int n, const T* base, int nv, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PolytopeT<T> p = desc[i];
+  if (p.numpoints != nv || p.coord != base + (size_t)i * nv * 3) *flag = 1;
+}
+
 }  // namespace ogjk

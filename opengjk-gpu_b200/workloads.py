@@ -108,11 +108,34 @@ def broadphase_pool(npoly: int, nverts: int, npairs: int, seed: int = 2024, dtyp
     rng = _rng(seed, 5)
     local = unit_sphere_hulls(npoly, nverts, seed, np.float64)
     radius = scale_range[0] + (scale_range[1] - scale_range[0]) * rng.random(npoly)
-    # box edge chosen so that the expected number of overlapping sphere pairs is ~npairs
-    mean_r3 = np.mean((radius[:, None] + radius[None, : min(npoly, 512)]) ** 3)
-    vol = (npoly * (npoly - 1) / 2.0) * (4.0 / 3.0) * np.pi * mean_r3 / max(npairs, 1)
-    edge = max(vol ** (1.0 / 3.0), 4.0 * scale_range[1])
-    centre = rng.random((npoly, 3)) * edge
+    # box edge chosen so that the number of overlapping sphere pairs is ~npairs.  The centres are confined to the box,
+    # so hulls near its faces have fewer neighbours than the unbounded-medium estimate assumes (at 20 000 hulls and
+    # 16 M pairs the box is only ~2 interaction diameters wide); the edge is therefore solved for by bisection on the
+    # exact pair count of a fixed random subsample of the hulls, scaled by (npoly / subsample)^2.
+    unit = rng.random((npoly, 3))
+    m = min(npoly, 3000)
+    sub = _rng(seed, 6).choice(npoly, size=m, replace=False) if m < npoly else np.arange(npoly)
+    rsum = radius[sub][:, None] + radius[sub][None, :]
+    iu = np.triu_indices(m, 1)
+    rsum2 = (rsum[iu] ** 2)
+    diff = unit[sub][:, None, :] - unit[sub][None, :, :]
+    d2_unit = np.einsum("ijk,ijk->ij", diff, diff)[iu]
+    scale_up = (npoly * (npoly - 1.0)) / max(m * (m - 1.0), 1.0)
+
+    def expected_pairs(edge_len):
+        return float(np.count_nonzero(d2_unit * (edge_len * edge_len) < rsum2)) * scale_up
+
+    lo_e, hi_e = 2.0 * scale_range[1], 2.0 * scale_range[1]
+    while expected_pairs(hi_e) > npairs and hi_e < 1e6:
+        hi_e *= 2.0
+    for _ in range(40):
+        mid = 0.5 * (lo_e + hi_e)
+        if expected_pairs(mid) > npairs:
+            lo_e = mid
+        else:
+            hi_e = mid
+    edge = lo_e  # slightly more than npairs; the list is truncated below
+    centre = unit * edge
     pool = (local * radius[:, None, None] + centre[:, None, :]).astype(dtype)
     # cell-list candidate search (host side; the generator is not the thing measured)
     cell = 2.0 * scale_range[1]

@@ -133,3 +133,55 @@ class Oracle:
                   self._p(dist), self._p(nrm), ctypes.c_int(int(do_gjk)), ctypes.c_int(int(do_epa)),
                   ctypes.c_int(nthreads))
         return simp, dist, nrm
+
+
+class RefGpu:
+    """The reference's own GPU library (GJK/gpu/openGJK.cu compiled unmodified for sm_100 by
+    oracle/build_ref_gpu.sh): second baseline ("kernel to beat") and second oracle.  fp32 only.  Needs a GPU."""
+
+    PATH = os.path.join(_HERE, "_ref_gpu", "libogjk_refgpu_f32.so")
+
+    @classmethod
+    def available(cls) -> bool:
+        return os.path.exists(cls.PATH)
+
+    def __init__(self):
+        if not self.available():
+            raise FileNotFoundError(f"{self.PATH} missing: run oracle/build_ref_gpu.sh where /root/reference exists")
+        self.lib = ctypes.CDLL(self.PATH)
+        self.dtype = np.dtype(np.float32)
+        self.sdtype = simplex_dtype(self.dtype)
+        assert self.lib.ogjk_refgpu_sizeof_real() == 4
+        assert self.lib.ogjk_refgpu_sizeof_simplex() == self.sdtype.itemsize
+
+    def gjk_epa(self, c1, c2, do_epa=True, reps=1):
+        """-> (simplices, distances, normals, gjk_ms, epa_ms); timing = cudaEvent pairs around the reference's
+        compute_minimum_distance_device / compute_epa_device, mean over `reps`."""
+        c1 = np.ascontiguousarray(c1, dtype=np.float32)
+        c2 = np.ascontiguousarray(c2, dtype=np.float32)
+        n = c1.shape[0]
+        simp = np.zeros(n, dtype=self.sdtype)
+        dist = np.zeros(n, dtype=np.float32)
+        nrm = np.zeros((n, 3), dtype=np.float32)
+        ms = (ctypes.c_float * 2)(0, 0)
+        rc = self.lib.ogjk_refgpu_gjk_epa(ctypes.c_long(n), Oracle._p(c1), ctypes.c_int(c1.shape[1]), Oracle._p(c2),
+                                          ctypes.c_int(c2.shape[1]), Oracle._p(simp), Oracle._p(dist), Oracle._p(nrm),
+                                          ctypes.c_int(int(do_epa)), ctypes.c_int(reps), ms)
+        if rc != 0:
+            raise RuntimeError(f"reference GPU library failed: cudaError {rc}")
+        return simp, dist, nrm, float(ms[0]), float(ms[1])
+
+    def gjk_epa_indexed(self, pool, pairs, do_epa=True, reps=1):
+        pool = np.ascontiguousarray(pool, dtype=np.float32)
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = pairs.shape[0]
+        simp = np.zeros(n, dtype=self.sdtype)
+        dist = np.zeros(n, dtype=np.float32)
+        nrm = np.zeros((n, 3), dtype=np.float32)
+        ms = (ctypes.c_float * 2)(0, 0)
+        rc = self.lib.ogjk_refgpu_gjk_epa_indexed(ctypes.c_int(pool.shape[0]), ctypes.c_int(pool.shape[1]), Oracle._p(pool),
+                                                  ctypes.c_long(n), Oracle._p(pairs), Oracle._p(simp), Oracle._p(dist),
+                                                  Oracle._p(nrm), ctypes.c_int(int(do_epa)), ctypes.c_int(reps), ms)
+        if rc != 0:
+            raise RuntimeError(f"reference GPU library failed: cudaError {rc}")
+        return simp, dist, nrm, float(ms[0]), float(ms[1])
