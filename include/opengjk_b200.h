@@ -53,7 +53,8 @@ int ogjk_set_sync(int enabled);
  * the three *_indexed host calls) split the pair range into one contiguous slice per device; a persistent host
  * thread per device runs the single-device path on its slice and copies the results straight into the caller's
  * arrays at the slice offset (indexed calls: the pool is replicated, the pair list sliced).  No collective, nothing
- * exchanged.  devices == NULL selects ordinals 0..count-1; count <= 1 restores single-device behaviour.  The same
+ * exchanged.  devices == NULL selects ordinals 0..count-1; count <= 1 restores single-device behaviour; a device
+ * listed more than once gets that many slices, run back to back.  The same
  * selection can be made without touching the caller's code through the environment: OGJK_DEVICES=all | <count> |
  * <i,j,...>.  Process-wide.  The *_device entry points always use the calling thread's current device. */
 int ogjk_set_devices(int count, const int* devices);
@@ -168,6 +169,12 @@ int ogjk_stage_times(double* gjk_ms, double* epa_ms, int* calls);
   int ogjk_##P##_compute_epa_indexed_device(int num_pairs, const void* d_polytopes, const void* d_pairs,       \
                                             void* d_simplices, OGJK_REAL* d_distances,                         \
                                             OGJK_REAL* d_contact_normals);                                     \
+  /* the two calls above in one (the device part of compute_gjk_epa_indexed, openGJK.cu:3274-3311, i.e. what the  \
+   * visualiser issues every physics step, integrate_final_gjk.cu:1028-1036); lets the library fuse the EPA gate    \
+   * into the GJK kernel and feeds ogjk_stage_times. */                                                             \
+  int ogjk_##P##_gjk_epa_indexed_device(int num_pairs, const void* d_polytopes, const void* d_pairs,           \
+                                        void* d_simplices, OGJK_REAL* d_distances,                             \
+                                        OGJK_REAL* d_contact_normals);                                         \
   /* reference: compute_epa_indexed, openGJK.h:473-481 (openGJK.cu:3235-3272) */                                \
   int ogjk_##P##_compute_epa_indexed(int num_polytopes, int num_pairs, const void* polytopes,                  \
                                      const void* pairs, void* simplices, OGJK_REAL* distances,                 \

@@ -178,6 +178,17 @@ class Engine:
                    _ptr(d_normals), _ptr(d_sub_mesh_body), ctypes.c_int(num_objects), _ptr(d_positions), _ptr(d_vel_ping),
                    _ptr(d_vel_pong), _ptr(d_ang_ping), _ptr(d_ang_pong), _ptr(d_quats), _ptr(d_inv_inertia), prm)
 
+    def set_devices(self, devices=None):
+        """devices the host-pointer calls fan out over (None / [] / one entry: single device); see ogjk_set_devices"""
+        devices = list(devices or [])
+        arr = (ctypes.c_int * max(len(devices), 1))(*devices)
+        if self.lib.ogjk_set_devices(ctypes.c_int(len(devices)), arr) != 0:
+            raise OgjkError(self.lib.ogjk_last_error().decode())
+
+    def release_cached_buffers(self):
+        if self.lib.ogjk_release_cached_buffers() != 0:
+            raise OgjkError(self.lib.ogjk_last_error().decode())
+
     def release_pool(self, d_polytopes):
         self.lib.ogjk_release_pool(_ptr(d_polytopes))
 
@@ -309,6 +320,11 @@ class Engine:
 
     def compute_epa_indexed_device(self, n, d_polytopes, d_pairs, d_simplices, d_distances, d_normals):
         self._call("compute_epa_indexed_device", ctypes.c_int(n), _ptr(d_polytopes), _ptr(d_pairs), _ptr(d_simplices),
+                   _ptr(d_distances), _ptr(d_normals))
+
+    def gjk_epa_indexed_device(self, n, d_polytopes, d_pairs, d_simplices, d_distances, d_normals):
+        """GJK then EPA over an indexed batch in one call (fused EPA gate; feeds stage_times)."""
+        self._call("gjk_epa_indexed_device", ctypes.c_int(n), _ptr(d_polytopes), _ptr(d_pairs), _ptr(d_simplices),
                    _ptr(d_distances), _ptr(d_normals))
 
     def free_indexed_device(self, d_polytopes, d_coords, d_pairs, d_simplices, d_distances, d_normals):

@@ -606,7 +606,11 @@ int launch_indexed_uniform(int n, const PoolInfo& pool, const CollisionPair* d_p
   IndexedSource<T> src{d_desc, d_pairs};
   const bool sync_saved = t_sync;
   t_sync = false;
-  int rc;
+  int rc = stage_mark(0);
+  if (rc) {
+    t_sync = sync_saved;
+    return rc;
+  }
   if (ws) {  // gate fused into the finisher warp
     int* scratch = nullptr;
     if ((rc = epa_scratch((size_t)n + 2, &scratch))) {
@@ -620,12 +624,16 @@ int launch_indexed_uniform(int n, const PoolInfo& pool, const CollisionPair* d_p
     }
     rc = launch_gjk_slots_ws<T>(n, nv, base, nv, base, simp, dist, nrm, scratch + 2, scratch, d_pairs);
     t_sync = sync_saved;
+    if (!rc) rc = stage_mark(1);
     if (!rc) rc = launch_epa_queue<T, IndexedSource<T>>(src, n, simp, dist, nrm, scratch + 2, scratch);
+    if (!rc) rc = stage_mark(2);
     return rc;
   }
   rc = launch_gjk_slots<T>(n, nv, base, nv, base, simp, dist, d_pairs);
   t_sync = sync_saved;
+  if (!rc) rc = stage_mark(1);
   if (!rc) rc = launch_epa<T>(src, n, simp, dist, nrm);
+  if (!rc) rc = stage_mark(2);
   return rc;
 }
 
@@ -1137,17 +1145,26 @@ int fan_out(const std::vector<int>& devs, const std::function<int(int, int)>& pa
   // one fan-out at a time per process: the workers (and their cached buffers) are shared
   static std::mutex fan_mutex;
   std::lock_guard<std::mutex> fan(fan_mutex);
-  for (int g = 0; g < G; ++g) g_workers[devs[g]]->submit([=] { return part(g, G); });
   int rc = 0;
   std::string first;
-  for (int g = 0; g < G; ++g) {
+  int pending[kMaxDevices];  // slice a worker is busy with, or -1 (a device listed twice runs its slices back to back)
+  for (int& x : pending) x = -1;
+  auto collect = [&](int dev) {
     std::string msg;
-    const int r = g_workers[devs[g]]->wait(&msg);
+    const int r = g_workers[dev]->wait(&msg);
     if (r && !rc) {
       rc = r;
-      first = "device " + std::to_string(devs[g]) + ": " + msg;
+      first = "device " + std::to_string(dev) + ": " + msg;
     }
+    pending[dev] = -1;
+  };
+  for (int g = 0; g < G; ++g) {
+    if (pending[devs[g]] >= 0) collect(devs[g]);
+    g_workers[devs[g]]->submit([=] { return part(g, G); });
+    pending[devs[g]] = g;
   }
+  for (int d = 0; d < kMaxDevices; ++d)
+    if (pending[d] >= 0) collect(d);
   if (rc) t_err = first;
   return rc;
 }
@@ -1357,9 +1374,7 @@ int ogjk_set_devices(int count, const int* devices) {
   for (int i = 0; i < count; ++i) {
     const int d = devices ? devices[i] : i;
     if (d < 0 || d >= have || d >= kMaxDevices) return fail_msg("ogjk_set_devices: device ordinal out of range");
-    for (int x : v)
-      if (x == d) return fail_msg("ogjk_set_devices: device listed twice");
-    v.push_back(d);
+    v.push_back(d);  // a device may be listed more than once: its slices then run back to back
   }
   std::lock_guard<std::mutex> lk(g_dev_mutex);
   g_devices = v;
@@ -1614,6 +1629,35 @@ long long ogjk_launch_count(int reset) {
     if (int rc = peek_numpoints<REAL>((const PolytopeT<REAL>*)d_polytopes, &nv)) return rc;                            \
     IndexedSource<REAL> src{(const PolytopeT<REAL>*)d_polytopes, (const CollisionPair*)d_pairs};                       \
     return launch_gjk_generic<REAL>(src, num_pairs, nv, (SimplexT<REAL>*)d_simplices, d_distances);                    \
+  }                                                                                                                    \
+  int ogjk_##P##_gjk_epa_indexed_device(int num_pairs, const void* d_polytopes, const void* d_pairs,                  \
+                                        void* d_simplices, REAL* d_distances, REAL* d_contact_normals) {              \
+    if (num_pairs <= 0) return 0;                                                                                      \
+    if (!d_contact_normals) return fail_msg("contact_normals must not be NULL on the device path");                    \
+    PoolInfo info;                                                                                                     \
+    if (num_pairs >= 32768 && lookup_pool(d_polytopes, &info)) {                                                       \
+      bool ok = false;                                                                                                 \
+      if (int rc = pool_layout_holds<REAL>(d_polytopes, info, info.count, &ok)) return rc;                             \
+      if (ok) {                                                                                                        \
+        const int fast = launch_indexed_uniform<REAL>(num_pairs, info, (const CollisionPair*)d_pairs,                  \
+                                                      (const PolytopeT<REAL>*)d_polytopes,                             \
+                                                      (SimplexT<REAL>*)d_simplices, d_distances, d_contact_normals,    \
+                                                      kGjkStage | kEpaStage);                                          \
+        if (fast <= 0) return fast;                                                                                    \
+      }                                                                                                                \
+    }                                                                                                                  \
+    int nv = 0;                                                                                                        \
+    if (int rc = peek_numpoints<REAL>((const PolytopeT<REAL>*)d_polytopes, &nv)) return rc;                            \
+    IndexedSource<REAL> src{(const PolytopeT<REAL>*)d_polytopes, (const CollisionPair*)d_pairs};                       \
+    const bool sync_saved = t_sync;                                                                                    \
+    t_sync = false;                                                                                                    \
+    int rc = stage_mark(0);                                                                                            \
+    if (!rc) rc = launch_gjk_generic<REAL>(src, num_pairs, nv, (SimplexT<REAL>*)d_simplices, d_distances);             \
+    t_sync = sync_saved;                                                                                               \
+    if (!rc) rc = stage_mark(1);                                                                                       \
+    if (!rc) rc = launch_epa<REAL>(src, num_pairs, (SimplexT<REAL>*)d_simplices, d_distances, d_contact_normals);      \
+    if (!rc) rc = stage_mark(2);                                                                                       \
+    return rc;                                                                                                         \
   }                                                                                                                    \
   int ogjk_##P##_compute_epa_indexed_device(int num_pairs, const void* d_polytopes, const void* d_pairs,              \
                                             void* d_simplices, REAL* d_distances, REAL* d_contact_normals) {          \
