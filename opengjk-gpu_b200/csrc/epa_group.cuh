@@ -16,7 +16,16 @@
 //   * reductions are 3-level xor butterflies on (value, lowest index);
 //   * face slot f belongs to lane f % G of the group; per-face passes run over the live slot range only;
 //   * both bodies' vertices are cached in registers (<= 64 per body: 8 per lane).
-// One warp per CTA (19 KB of shared memory for its four work areas), 11 CTAs per SM.
+// One warp per CTA.
+//
+// Work area.  With the full-size EpaWork (4.7 KB, room for the reference's 64 iterations / 128 faces) only ~11 warps
+// fit an SM and the kernel is latency-bound (profiles/r1e_experiments.txt).  The measured distribution of EPA
+// iterations is short-tailed (config 3: mean 12.8, 99.5 % <= 24; configs 2 and 5: 99.9 % <= 25), so the default work
+// area is EpaWorkSmall: 28 vertices, 56 face slots, 48 dying-face edges -- 1.7 KB (fp32).  A pair that would exceed
+// any of the three capacities is abandoned untouched (EPA writes its outputs only when it reports) and appended to an
+// overflow queue, which the warp-per-pair kernel with the full-size work area then processes from scratch; the
+// result is therefore the same as if every pair had had the full-size area.  With 1.7 KB per pair, G = 4 lanes per
+// pair (eight pairs per warp) runs 16 warps per SM and G = 8 about 30.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,9 +34,23 @@
 
 namespace ogjk {
 
+template <typename T>
+struct EpaWorkSmall {
+  using real = T;
+  static constexpr int kVerts = 28, kFaces = 56, kEdges = 48;
+  static constexpr bool kSmall = true;
+  T vx[kVerts], vy[kVerts], vz[kVerts];
+  uint16_t src1[kVerts], src2[kVerts];  // bodies of up to 65 535 vertices (the launcher checks)
+  T nx[kFaces], ny[kFaces], nz[kFaces];
+  T fd[kFaces];
+  uint32_t fv[kFaces];
+  uint16_t edge[kEdges];
+  uint8_t rank2slot[kEdges];  // only the first `number of horizon edges` ranks are ever looked up
+};
+
 template <int G>
 struct Grp {
-  static_assert(G == 8 || G == 16 || G == 32, "group size");
+  static_assert(G == 4 || G == 8 || G == 16 || G == 32, "group size");
   int lane;       // lane within the group
   unsigned mask;  // warp lane mask of the group
   int shift;      // first warp lane of the group
@@ -75,29 +98,29 @@ OGJK_D void grp_argmin(const Grp<G>& g, T& best, int& bi) {
 }
 
 // this lane's share of a body: vertices lane, lane + G, ... (cached in registers when the body has <= 64 vertices)
-template <typename T, int G>
+template <typename T, int G, int KV>
 struct GrpVerts {
-  static constexpr int kPerLane = 64 / G;
+  static constexpr int kPerLane = KV;
   V3<T> p[kPerLane];
   bool cached;
 };
-template <typename T, int G>
-OGJK_D void cache_grp_verts(const BodyRef<T>& A, int glane, GrpVerts<T, G>& r) {
-  r.cached = A.n <= 64;
+template <typename T, int G, int KV>
+OGJK_D void cache_grp_verts(const BodyRef<T>& A, int glane, GrpVerts<T, G, KV>& r) {
+  r.cached = A.n <= G * KV;
 #pragma unroll
-  for (int k = 0; k < GrpVerts<T, G>::kPerLane; ++k) {
+  for (int k = 0; k < KV; ++k) {
     const int i = glane + G * k;
     r.p[k] = (r.cached && i < A.n) ? load3(A.c, i) : mk<T>(T(0), T(0), T(0));
   }
 }
-template <typename T, int G>
-OGJK_D void grp_lane_support(const BodyRef<T>& A, const GrpVerts<T, G>& L, const V3<T>& d, bool negate, int glane,
+template <typename T, int G, int KV>
+OGJK_D void grp_lane_support(const BodyRef<T>& A, const GrpVerts<T, G, KV>& L, const V3<T>& d, bool negate, int glane,
                              T& best, int& bi) {
   best = (T)-1e10f;
   bi = 0x7fffffff;
   if (L.cached) {
 #pragma unroll
-    for (int k = 0; k < GrpVerts<T, G>::kPerLane; ++k) {
+    for (int k = 0; k < KV; ++k) {
       const int i = glane + G * k;
       T sv = dot(L.p[k].x, L.p[k].y, L.p[k].z, d);
       if (negate) sv = -sv;
@@ -119,13 +142,13 @@ OGJK_D void grp_lane_support(const BodyRef<T>& A, const GrpVerts<T, G>& L, const
   }
 }
 // EPA.c:307-344 (see epa_support)
-template <typename T, int G>
-OGJK_D bool grp_support(const Grp<G>& g, const BodyRef<T>& A, const BodyRef<T>& B, const GrpVerts<T, G>& LA,
-                        const GrpVerts<T, G>& LB, const V3<T>& d, V3<T>& w, int& i1, int& i2) {
+template <typename T, int G, int KV>
+OGJK_D bool grp_support(const Grp<G>& g, const BodyRef<T>& A, const BodyRef<T>& B, const GrpVerts<T, G, KV>& LA,
+                        const GrpVerts<T, G, KV>& LB, const V3<T>& d, V3<T>& w, int& i1, int& i2) {
   T b1, b2;
   int k1, k2;
-  grp_lane_support<T, G>(A, LA, d, false, g.lane, b1, k1);
-  grp_lane_support<T, G>(B, LB, d, true, g.lane, b2, k2);
+  grp_lane_support<T, G, KV>(A, LA, d, false, g.lane, b1, k1);
+  grp_lane_support<T, G, KV>(B, LB, d, true, g.lane, b2, k2);
   grp_argmax<T, G>(g, b1, k1);
   grp_argmax<T, G>(g, b2, k2);
   if (k1 == 0x7fffffff || k2 == 0x7fffffff) return false;
@@ -137,13 +160,13 @@ OGJK_D bool grp_support(const Grp<G>& g, const BodyRef<T>& A, const BodyRef<T>& 
 
 // closest live face among slots [0, G*nj): smallest distance >= 0, lowest slot on ties (EPA.c:606-617); -1 if none
 // `trips` >= nj is the loop bound (equal to nj, or the maximum over the warp's groups when they run in lock step)
-template <typename T, int G>
-OGJK_D int grp_closest_face(const Grp<G>& g, const EpaWork<T>& W, int nj, int trips, T& dist) {
+template <typename T, int G, typename WT>
+OGJK_D int grp_closest_face(const Grp<G>& g, const WT& W, int nj, int trips, T& dist) {
   T best = (T)1e10f;
   int bf = 0x7fffffff;
   for (int j = 0; j < trips; ++j) {
-    if (j < nj) {
-      const int f = g.lane + G * j;
+    const int f = g.lane + G * j;
+    if (j < nj && f < WT::kFaces) {
       const bool live = (W.fv[f] >> 24) != 0;
       const T d = W.fd[f];
       if (live && d >= T(0) && d < best) {
@@ -163,15 +186,19 @@ struct EpaGroupConfig {
   static constexpr int kThreads = 32;  // one warp per CTA: kThreads / kGroup work areas
 };
 
-template <typename T, int G, typename Source>
-__global__ void __launch_bounds__(EpaGroupConfig<T>::kThreads, (G == 16 && sizeof(T) == 4) ? 20 : 1)
+// KV: vertices per lane of each body cached in registers (bodies of up to G * KV vertices; larger ones are read from
+// global memory on every support search).  WT: work area type (EpaWork<T> or EpaWorkSmall<T>).  counters: [0] queued
+// pairs, [1] ticket, [2] overflow count (small work area only: pairs appended to `overflow`).
+template <typename T, int G, int KV, typename WT, int MINB, typename Source>
+__global__ void __launch_bounds__(EpaGroupConfig<T>::kThreads, MINB)
 epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
-                 T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters) {
+                 T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters,
+                 int* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char epa_smem[];
-  EpaWork<T>* work = reinterpret_cast<EpaWork<T>*>(epa_smem);
+  WT* work = reinterpret_cast<WT*>(epa_smem);
   const int wlane = threadIdx.x & 31;
   const Grp<G> g(wlane);
-  EpaWork<T>& W = work[threadIdx.x / G];
+  WT& W = work[threadIdx.x / G];
   const int count = counters[0];
   const T eps = Tol<T>::eps();
   const T tol = Tol<T>::eps_tot();
@@ -185,7 +212,7 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
   BodyRef<T> A, B;
   A.c = B.c = nullptr;
   A.n = B.n = 0;
-  GrpVerts<T, G> LA, LB;
+  GrpVerts<T, G, KV> LA, LB;
   LA.cached = LB.cached = false;
   int nv_in = 0, nv = 0, iter = 0, hi = 4;
   V3<T> centroid = mk<T>(T(0), T(0), T(0));
@@ -206,9 +233,11 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         sp = simplices + pair;
         nrm_out = normals + 3 * (size_t)pair;
         src.get(pair, A, B);
-        cache_grp_verts<T, G>(A, g.lane, LA);
-        cache_grp_verts<T, G>(B, g.lane, LB);
+        cache_grp_verts<T, G, KV>(A, g.lane, LA);
+        cache_grp_verts<T, G, KV>(B, g.lane, LB);
         g.sync();  // the previous pair's last reads of the work area are done
+        const bool oversize = WT::kSmall && (A.n > 65535 || B.n > 65535);  // provenance is kept in 16 bits
+        if (oversize && g.lane == 0) overflow[atomicAdd(&counters[2], 1)] = (int)pair;  // phase stays kIdle
         nv_in = sp->nvrtx;
         nv = nv_in;
         if (g.lane < 4) {
@@ -257,12 +286,12 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         };
 
         // ---- regrow a degenerate simplex to a tetrahedron (EPA.c:375-583) -----------------------------------------
-        bool ok_setup = true;
-        if (nv != 4) {
+        bool ok_setup = !oversize;
+        if (ok_setup && nv != 4) {
           V3<T> p;
           int i1 = 0, i2 = 0;
           if (ok_setup && nv == 1) {
-            const bool ok = grp_support<T, G>(g, A, B, LA, LB, work_vertex(W, 0), p, i1, i2);
+            const bool ok = grp_support<T, G, KV>(g, A, B, LA, LB, work_vertex(W, 0), p, i1, i2);
             if (ok && is_new(p)) push(p, i1, i2);
             else { touch_exit(i1, i2); ok_setup = false; }
           }
@@ -273,19 +302,19 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
             if (len > eps && fabs_(edge.x) > mul_rn((T)0.9f, len)) axis = mk<T>(T(0), T(1), T(0));
             V3<T> dir = cross(edge, axis);
             if (norm2(dir) < eps) dir = cross(edge, mk<T>(T(0), T(0), T(1)));
-            const bool ok = grp_support<T, G>(g, A, B, LA, LB, dir, p, i1, i2);
+            const bool ok = grp_support<T, G, KV>(g, A, B, LA, LB, dir, p, i1, i2);
             if (ok && is_new(p)) push(p, i1, i2);
             else { touch_exit(i1, i2); ok_setup = false; }
           }
           if (ok_setup && nv == 3) {
             const V3<T> v0 = work_vertex(W, 0);
             V3<T> dir = cross(vsub(work_vertex(W, 1), v0), vsub(work_vertex(W, 2), v0));
-            bool ok = grp_support<T, G>(g, A, B, LA, LB, dir, p, i1, i2);
+            bool ok = grp_support<T, G, KV>(g, A, B, LA, LB, dir, p, i1, i2);
             if (ok && is_new(p)) {
               push(p, i1, i2);
             } else {
               dir = vneg(dir);
-              ok = grp_support<T, G>(g, A, B, LA, LB, dir, p, i1, i2);
+              ok = grp_support<T, G, KV>(g, A, B, LA, LB, dir, p, i1, i2);
               if (ok && is_new(p)) push(p, i1, i2);
               else { touch_exit(i1, i2); ok_setup = false; }
             }
@@ -305,7 +334,7 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
             centroid.y = add_rn(centroid.y, mul_rn(W.vy[q2], (T)0.25f));
             centroid.z = add_rn(centroid.z, mul_rn(W.vz[q2], (T)0.25f));
           }
-          for (int f = g.lane; f < kEpaMaxFaces; f += G) W.fv[f] = 0u;
+          for (int f = g.lane; f < WT::kFaces; f += G) W.fv[f] = 0u;
           g.sync();
           if (g.lane < 4) {
             // faces (0,1,2) (0,3,1) (0,2,3) (1,3,2)
@@ -339,7 +368,8 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
       if (__any_sync(0xffffffffu, act && iter >= kEpaMaxIters)) {  // iteration cap (EPA.c:828-863): rare
         const bool cap = act && iter >= kEpaMaxIters;
         T cd;
-        const int cf = grp_closest_face<T, G>(gw, W, cap ? kEpaMaxFaces / G : 0, kEpaMaxFaces / G, cd);
+        constexpr int kAllTrips = (WT::kFaces + G - 1) / G;
+        const int cf = grp_closest_face<T, G, WT>(gw, W, cap ? kAllTrips : 0, kAllTrips, cd);
         if (cap) {
           if (cf >= 0) {
             reported = true;
@@ -354,7 +384,7 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
       const int nj = act ? (hi + G - 1) / G : 0;
       const int njw = __reduce_max_sync(0xffffffffu, nj);
       T cd;
-      int cf = grp_closest_face<T, G>(gw, W, nj, njw, cd);
+      int cf = grp_closest_face<T, G, WT>(gw, W, nj, njw, cd);
       if (act && cf < 0) {
         phase = kReport;
         act = false;
@@ -367,8 +397,8 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         T b1 = (T)-1e10f, b2 = (T)-1e10f;
         int k1 = 0x7fffffff, k2 = 0x7fffffff;
         if (act) {  // no collective inside; idle groups may hold stale body descriptors
-          grp_lane_support<T, G>(A, LA, cn, false, g.lane, b1, k1);
-          grp_lane_support<T, G>(B, LB, cn, true, g.lane, b2, k2);
+          grp_lane_support<T, G, KV>(A, LA, cn, false, g.lane, b1, k1);
+          grp_lane_support<T, G, KV>(B, LB, cn, true, g.lane, b2, k2);
         }
         grp_argmax<T, G>(gw, b1, k1);
         grp_argmax<T, G>(gw, b2, k2);
@@ -400,6 +430,13 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         report_face = cf;
         report_d = cd;
         phase = kReport;
+        act = false;
+      }
+
+      // small work area: a pair that needs more than its capacities is handed to the full-size kernel untouched
+      bool ovf = false;
+      if (WT::kSmall && act && nv >= WT::kVerts) {
+        ovf = true;
         act = false;
       }
 
@@ -435,14 +472,21 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         if (sees) {
           const int rank = nvis + __popc(vm & g.below());
           const uint32_t a = word & 0xff, b = (word >> 8) & 0xff, c = (word >> 16) & 0xff;
-          W.edge[3 * rank + 0] = (uint16_t)((a << 8) | b);
-          W.edge[3 * rank + 1] = (uint16_t)((b << 8) | c);
-          W.edge[3 * rank + 2] = (uint16_t)((c << 8) | a);
+          if (3 * rank + 2 < WT::kEdges) {
+            W.edge[3 * rank + 0] = (uint16_t)((a << 8) | b);
+            W.edge[3 * rank + 1] = (uint16_t)((b << 8) | c);
+            W.edge[3 * rank + 2] = (uint16_t)((c << 8) | a);
+          }
           W.fv[f] = word & 0x00ffffffu;  // retire
         }
         nvis += __popc(vm);
       }
       __syncwarp();
+      if (WT::kSmall && act && 3 * nvis > WT::kEdges) {  // more dying faces than the edge list holds
+        ovf = true;
+        act = false;
+        nvis = 0;
+      }
       const int nedge = 3 * nvis;  // 0 for inactive groups
       const int nedgew = __reduce_max_sync(0xffffffffu, nedge);
 
@@ -450,13 +494,14 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
       // enough -- unless the 128 slots run out, in which case the remaining edges are dropped (EPA.c:775)
       int nfree = 0;
       {
-        const int limit = !act ? 0 : (hi + nedge < kEpaMaxFaces ? hi + nedge : kEpaMaxFaces);
+        const int limit = !act ? 0 : (hi + nedge < WT::kFaces ? hi + nedge : WT::kFaces);
         const int limitw = __reduce_max_sync(0xffffffffu, limit);
         for (int j = 0; G * j < limitw; ++j) {
           const int f = g.lane + G * j;
-          const bool is_free = G * j < limit && (W.fv[f] >> 24) == 0;
+          const bool is_free = f < limit && (W.fv[f] >> 24) == 0;
           const unsigned fm = gw.ballot(is_free);
-          if (is_free) W.rank2slot[nfree + __popc(fm & g.below())] = (uint8_t)f;
+          const int r = nfree + __popc(fm & g.below());
+          if (is_free && (!WT::kSmall || r < WT::kEdges)) W.rank2slot[r] = (uint8_t)f;
           nfree += __popc(fm);
         }
       }
@@ -493,6 +538,16 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         }
         base_rank += __popc(keepm);
       }
+      if (WT::kSmall && act && base_rank > nfree) {  // ran out of the small area's face slots: the full-size area has more
+        ovf = true;
+        act = false;
+      }
+      if (WT::kSmall && gw.any(ovf)) {  // (warp-uniform branch: every group looks at its own lanes' bits)
+        if (ovf) {
+          if (g.lane == 0) overflow[atomicAdd(&counters[2], 1)] = (int)pair;
+          phase = kIdle;
+        }
+      }
       if (act) {
         const int used = base_rank < nfree ? base_rank : nfree;
         if (used > 0) {
@@ -506,7 +561,7 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
       if (__any_sync(0xffffffffu, any_degenerate)) {
         const bool mine = gw.any(any_degenerate);
         if (mine)
-          for (int f = g.lane; f < kEpaMaxFaces; f += G)
+          for (int f = g.lane; f < WT::kFaces; f += G)
             if ((W.fv[f] >> 24) && W.fd[f] == (T)1e10) W.fv[f] &= 0x00ffffffu;
         __syncwarp();
       }

@@ -39,6 +39,9 @@ struct EpaConfig<double> {
 
 template <typename T>
 struct EpaWork {
+  using real = T;
+  static constexpr int kVerts = kEpaMaxVerts, kFaces = kEpaMaxFaces, kEdges = kEpaMaxFaces * 3;
+  static constexpr bool kSmall = false;
   T vx[kEpaMaxVerts], vy[kEpaMaxVerts], vz[kEpaMaxVerts];  // Minkowski-difference vertices
   int src1[kEpaMaxVerts], src2[kEpaMaxVerts];              // provenance: vertex index on body 1 / body 2
   T nx[kEpaMaxFaces], ny[kEpaMaxFaces], nz[kEpaMaxFaces];  // unit outward normals
@@ -196,16 +199,17 @@ OGJK_D void origin_barycentric(const V3<T>& v0, const V3<T>& v1, const V3<T>& v2
   }
 }
 
-template <typename T>
-OGJK_D V3<T> work_vertex(const EpaWork<T>& W, int i) {
-  return mk<T>(W.vx[i], W.vy[i], W.vz[i]);
+template <typename WT>
+OGJK_D V3<typename WT::real> work_vertex(const WT& W, int i) {
+  return mk<typename WT::real>(W.vx[i], W.vy[i], W.vz[i]);
 }
 
 // Build face `f` = (a, b, c): orient it away from the centroid (EPA.c:203-232, 791-819), then compute its plane
 // (EPA.c:92-129).  Returns the packed vertex word with the live bit set; a degenerate face is reported through
 // `degenerate` and is retired by the caller once all slots of this iteration are assigned.
-template <typename T>
-OGJK_D uint32_t make_face(EpaWork<T>& W, int f, int a, int b, int c, const V3<T>& centroid, bool& degenerate) {
+template <typename WT>
+OGJK_D uint32_t make_face(WT& W, int f, int a, int b, int c, const V3<typename WT::real>& centroid, bool& degenerate) {
+  using T = typename WT::real;
   const V3<T> va = work_vertex(W, a), vb = work_vertex(W, b), vc = work_vertex(W, c);
   const V3<T> e0 = vsub(vb, va), e1 = vsub(vc, va);
   V3<T> nrm = cross(e0, e1);

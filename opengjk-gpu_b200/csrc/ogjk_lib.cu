@@ -393,61 +393,88 @@ int launch_gjk_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, Simple
 }
 
 // ---- scratch for the EPA work queue ------------------------------------------------------------------------------
-int epa_scratch(size_t ints, int** out) {
+// counters: [0] queued pairs, [1] ticket of the first EPA kernel, [2] overflow count, [3] ticket of the overflow pass
+struct EpaQueue {
+  int* counters = nullptr;
+  int* queue = nullptr;     // n entries: colliding pairs, appended by the gate
+  int* overflow = nullptr;  // n entries: pairs the small-work-area kernel handed back
+};
+int epa_queue_buffers(size_t n, EpaQueue* q) {
   StreamScratch* ss = nullptr;
   if (int rc = stream_scratch(&ss)) return rc;
-  return scratch_grow(ss->epa, ints, out);
+  int* p = nullptr;
+  if (int rc = scratch_grow(ss->epa, 2 * n + 4, &p)) return rc;
+  q->counters = p;
+  q->queue = p + 4;
+  q->overflow = p + 4 + n;
+  OGJK_CK(cudaMemsetAsync(p, 0, 4 * sizeof(int), t_stream));
+  return 0;
 }
 
-template <typename T, int G, typename Source>
-int launch_epa_group(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distances, T* d_normals, const int* queue,
-                     int* counters, int sms) {
-  constexpr int threads = EpaGroupConfig<T>::kThreads;
-  constexpr int groups = threads / G;
-  const size_t smem = (size_t)groups * sizeof(EpaWork<T>);
+template <typename T, typename Source>
+int launch_epa_warp_queue(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distances, T* d_normals,
+                          const int* queue, int* counters, int sms) {
+  constexpr int wpb = EpaConfig<T>::kWarpsPerBlock;
   int per_sm = 0;
-  auto kern = epa_group_kernel<T, G, Source>;
-  OGJK_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_queue_kernel<T, Source>, wpb * 32, 0));
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)sms * per_sm;
-  const long long need = ((long long)n + groups - 1) / groups;
+  const long long need = ((long long)n + wpb - 1) / wpb;
   if (grid > need) grid = need;
-  kern<<<(unsigned)grid, threads, smem, t_stream>>>(src, d_simplices, d_distances, d_normals, queue, counters);
-  return finish_launch("epa group kernel");
+  epa_queue_kernel<T, Source><<<(unsigned)grid, wpb * 32, 0, t_stream>>>(src, d_simplices, d_distances, d_normals, queue,
+                                                                        counters);
+  return finish_launch("epa kernel");
 }
 
-// persistent EPA over a device-side queue of colliding pairs (counters[0] = queued pairs, counters[1] = ticket).
-// Default: one warp per pair.  OGJK_EPA_KERNEL=group selects the sub-warp group kernel (8 lanes per pair, four pairs per
-// warp in lock step, epa_group.cuh): 38 % fewer warp instructions per pair but, at 11 warps per SM, latency-bound --
-// 8.6 ms against 8.4 ms for 1 Mi overlapping 32-vertex pairs on B200, so it is not the default yet.
+template <typename T, int G, int KV, typename WT, int MINB, typename Source>
+int launch_epa_group(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distances, T* d_normals, const EpaQueue& q,
+                     int sms) {
+  constexpr int threads = EpaGroupConfig<T>::kThreads;
+  constexpr int groups = threads / G;
+  const size_t smem = (size_t)groups * sizeof(WT);
+  auto kern = epa_group_kernel<T, G, KV, WT, MINB, Source>;
+  long long grid = 0;
+  if (int rc = persistent_grid(kern, threads, smem, &grid)) return rc;
+  const long long need = ((long long)n + groups - 1) / groups;
+  if (grid > need) grid = need;
+  const bool sync_saved = t_sync;
+  if (WT::kSmall) t_sync = false;  // the overflow pass follows
+  kern<<<(unsigned)grid, threads, smem, t_stream>>>(src, d_simplices, d_distances, d_normals, q.queue, q.counters, q.overflow);
+  int rc = finish_launch("epa group kernel");
+  t_sync = sync_saved;
+  if (rc || !WT::kSmall) return rc;
+  // pairs that did not fit the small work area (a fraction of a percent): warp-per-pair kernel, full-size area
+  return launch_epa_warp_queue<T, Source>(src, n, d_simplices, d_distances, d_normals, q.overflow, q.counters + 2, sms);
+}
+
+// Persistent EPA over a device-side queue of colliding pairs.  Default: the sub-warp group kernel with the small work
+// area -- G = 4 lanes per pair for bodies of up to 32 vertices, G = 8 up to 64 -- followed by the overflow pass; larger
+// bodies (the support scan dominates) and OGJK_EPA_KERNEL=warp take one warp per pair.  Development overrides:
+// OGJK_EPA_KERNEL=warp|group (group = full-size work area, 8 lanes)|small4|small8.
 template <typename T, typename Source>
-int launch_epa_queue(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distances, T* d_normals, const int* queue,
-                     int* counters) {
-  int dev = 0, sms = 0, per_sm = 0;
+int launch_epa_queue(const Source& src, int n, int nv_hint, SimplexT<T>* d_simplices, T* d_distances, T* d_normals,
+                     const EpaQueue& q) {
+  int dev = 0, sms = 0;
   OGJK_CK(cudaGetDevice(&dev));
   OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const char* e = getenv("OGJK_EPA_KERNEL");
-  if (!(e && !strcmp(e, "group"))) {
-    constexpr int wpb = EpaConfig<T>::kWarpsPerBlock;
-    OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_queue_kernel<T, Source>, wpb * 32, 0));
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)sms * per_sm;
-    const long long need = ((long long)n + wpb - 1) / wpb;
-    if (grid > need) grid = need;
-    epa_queue_kernel<T, Source><<<(unsigned)grid, wpb * 32, 0, t_stream>>>(src, d_simplices, d_distances, d_normals,
-                                                                          queue, counters);
-    return finish_launch("epa kernel");
+  int mode = nv_hint <= 32 ? 4 : nv_hint <= 64 ? 8 : 0;  // 0 warp per pair, 4 / 8 small work area, 1 full-size group
+  if (e) mode = !strcmp(e, "warp") ? 0 : !strcmp(e, "group") ? 1 : !strcmp(e, "small4") ? 4 : !strcmp(e, "small8") ? 8 : mode;
+  constexpr int minb = sizeof(T) == 4 ? 16 : 8;
+  if (mode == 4) {
+    if (nv_hint <= 16)
+      return launch_epa_group<T, 4, 4, EpaWorkSmall<T>, minb, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
+    return launch_epa_group<T, 4, 8, EpaWorkSmall<T>, minb, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
   }
-  const char* eg = getenv("OGJK_EPA_GROUP");  // development: lanes per pair of the group kernel (8 or 16)
-  if (eg && atoi(eg) == 16) return launch_epa_group<T, 16, Source>(src, n, d_simplices, d_distances, d_normals, queue, counters, sms);
-  return launch_epa_group<T, 8, Source>(src, n, d_simplices, d_distances, d_normals, queue, counters, sms);
+  if (mode == 8) return launch_epa_group<T, 8, 8, EpaWorkSmall<T>, minb, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
+  if (mode == 1) return launch_epa_group<T, 8, 8, EpaWork<T>, 1, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
+  return launch_epa_warp_queue<T, Source>(src, n, d_simplices, d_distances, d_normals, q.queue, q.counters, sms);
 }
 
 // EPA launch: small batches get one warp per pair; large ones go through gate + compaction + a persistent
 // queue kernel so that only colliding pairs occupy warps.
 template <typename T, typename Source>
-int launch_epa(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distances, T* d_normals) {
+int launch_epa(const Source& src, int n, int nv_hint, SimplexT<T>* d_simplices, T* d_distances, T* d_normals) {
   if (!d_normals) return fail_msg("contact_normals must not be NULL on the device path");
   constexpr int wpb = EpaConfig<T>::kWarpsPerBlock;
   if (n < 8192) {
@@ -455,16 +482,13 @@ int launch_epa(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distance
     epa_kernel<T, Source><<<grid, wpb * 32, 0, t_stream>>>(src, d_simplices, d_distances, d_normals, n);
     return finish_launch("epa kernel");
   }
-  int* scratch = nullptr;
-  if (int rc = epa_scratch((size_t)n + 2, &scratch)) return rc;
-  int* counters = scratch;  // [0] = queued pairs, [1] = ticket
-  int* queue = scratch + 2;
-  OGJK_CK(cudaMemsetAsync(counters, 0, 2 * sizeof(int), t_stream));
+  EpaQueue q;
+  if (int rc = epa_queue_buffers((size_t)n, &q)) return rc;
   epa_gate_kernel<T><<<(unsigned)(((long long)n + 255) / 256), 256, 0, t_stream>>>(d_simplices, d_distances, d_normals, n,
-                                                                            queue, counters);
+                                                                            q.queue, q.counters);
   ++t_launches;
   OGJK_CK(cudaGetLastError());
-  return launch_epa_queue<T, Source>(src, n, d_simplices, d_distances, d_normals, queue, counters);
+  return launch_epa_queue<T, Source>(src, n, nv_hint, d_simplices, d_distances, d_normals, q);
 }
 
 // GJK then EPA on a dense uniform device batch.  When the warp-specialised slot kernel applies, its finisher warp
@@ -493,15 +517,14 @@ int launch_gjk_epa_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, Si
     const bool aligned = (((uintptr_t)c1 | (uintptr_t)c2) & 15u) == 0 && nv1 % 4 == 0 && nv2 % 4 == 0;
     const int force = forced_kernel();
     if (aligned && n >= 32768 && (force == 0 || force == 4) && use_ws_kernel(nv1, nv2, (int)sizeof(T))) {
-      int* scratch = nullptr;
-      if (int rc = epa_scratch((size_t)n + 2, &scratch)) return rc;
-      OGJK_CK(cudaMemsetAsync(scratch, 0, 2 * sizeof(int), t_stream));
+      EpaQueue q;
+      if (int rc = epa_queue_buffers((size_t)n, &q)) return rc;
       const bool sync_saved = t_sync;
       t_sync = false;  // no need to synchronise between the two stages
-      int rc = launch_gjk_slots_ws<T>(n, nv1, c1, nv2, c2, simp, dist, nrm, scratch + 2, scratch);
+      int rc = launch_gjk_slots_ws<T>(n, nv1, c1, nv2, c2, simp, dist, nrm, q.queue, q.counters);
       t_sync = sync_saved;
       if (!rc) rc = stage_mark(1);
-      if (!rc) rc = launch_epa_queue<T, UniformSource<T>>(src, n, simp, dist, nrm, scratch + 2, scratch);
+      if (!rc) rc = launch_epa_queue<T, UniformSource<T>>(src, n, nv1 > nv2 ? nv1 : nv2, simp, dist, nrm, q);
       if (!rc) rc = stage_mark(2);
       return rc;
     }
@@ -512,7 +535,7 @@ int launch_gjk_epa_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, Si
   if (rc > 0) rc = launch_gjk_generic<T>(src, n, (nv1 + nv2) / 2, simp, dist);
   t_sync = sync_saved;
   if (!rc) rc = stage_mark(1);
-  if (!rc) rc = launch_epa<T>(src, n, simp, dist, nrm);
+  if (!rc) rc = launch_epa<T>(src, n, nv1 > nv2 ? nv1 : nv2, simp, dist, nrm);
   if (!rc) rc = stage_mark(2);
   return rc;
 }
@@ -612,27 +635,22 @@ int launch_indexed_uniform(int n, const PoolInfo& pool, const CollisionPair* d_p
     return rc;
   }
   if (ws) {  // gate fused into the finisher warp
-    int* scratch = nullptr;
-    if ((rc = epa_scratch((size_t)n + 2, &scratch))) {
+    EpaQueue q;
+    if ((rc = epa_queue_buffers((size_t)n, &q))) {
       t_sync = sync_saved;
       return rc;
     }
-    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * sizeof(int), t_stream);
-    if (e != cudaSuccess) {
-      t_sync = sync_saved;
-      return fail("cudaMemsetAsync", e);
-    }
-    rc = launch_gjk_slots_ws<T>(n, nv, base, nv, base, simp, dist, nrm, scratch + 2, scratch, d_pairs);
+    rc = launch_gjk_slots_ws<T>(n, nv, base, nv, base, simp, dist, nrm, q.queue, q.counters, d_pairs);
     t_sync = sync_saved;
     if (!rc) rc = stage_mark(1);
-    if (!rc) rc = launch_epa_queue<T, IndexedSource<T>>(src, n, simp, dist, nrm, scratch + 2, scratch);
+    if (!rc) rc = launch_epa_queue<T, IndexedSource<T>>(src, n, nv, simp, dist, nrm, q);
     if (!rc) rc = stage_mark(2);
     return rc;
   }
   rc = launch_gjk_slots<T>(n, nv, base, nv, base, simp, dist, d_pairs);
   t_sync = sync_saved;
   if (!rc) rc = stage_mark(1);
-  if (!rc) rc = launch_epa<T>(src, n, simp, dist, nrm);
+  if (!rc) rc = launch_epa<T>(src, n, nv, simp, dist, nrm);
   if (!rc) rc = stage_mark(2);
   return rc;
 }
@@ -907,7 +925,7 @@ int run_pairs_host_dense(int n, const PolytopeT<T>* bd1, const PolytopeT<T>* bd2
       if ((stages & kEpa) && !(stages & kGjk)) {
         OGJK_CK(cudaMemsetAsync(d_nrm + lo * 3, 0, (size_t)m * 3 * sizeof(T), P.s_comp));
         UniformSource<T> src{d_c1 + lo * nv1 * 3, d_c2 + lo * nv2 * 3, nv1, nv2};
-        if (int rc = launch_epa<T>(src, m, d_simp + lo, d_dist + lo, d_nrm + lo * 3)) return rc;
+        if (int rc = launch_epa<T>(src, m, nv1 > nv2 ? nv1 : nv2, d_simp + lo, d_dist + lo, d_nrm + lo * 3)) return rc;
       }
     }
     OGJK_CK(cudaEventRecord(P.ev_done[k], P.s_comp));
@@ -965,7 +983,7 @@ int run_pairs_host(int n, const PolytopeT<T>* bd1, const PolytopeT<T>* bd2, Simp
       DescSource<T> src{f1.d_desc, f2.d_desc};
       const int hint = (int)((f1.max_nv + f2.max_nv) / 2);
       if ((stages & kGjk) && (rc = launch_gjk_generic<T>(src, n, hint, d_simp, d_dist))) break;
-      if ((stages & kEpa) && (rc = launch_epa<T>(src, n, d_simp, d_dist, d_nrm))) break;
+      if ((stages & kEpa) && (rc = launch_epa<T>(src, n, (int)(f1.max_nv > f2.max_nv ? f1.max_nv : f2.max_nv), d_simp, d_dist, d_nrm))) break;
     }
     if ((e = cudaMemcpyAsync(distances, d_dist, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, t_stream)) != cudaSuccess) { rc = fail("D2H distances", e); break; }
     if ((e = cudaMemcpyAsync(simplices, d_simp, (size_t)n * sizeof(SimplexT<T>), cudaMemcpyDeviceToHost, t_stream)) != cudaSuccess) { rc = fail("D2H simplices", e); break; }
@@ -1033,7 +1051,7 @@ int run_indexed_host(int num_polytopes, int num_pairs, const PolytopeT<T>* polyt
       if (rc == 1) {  // not a uniform fp32 pool / small batch: the general kernels
         rc = 0;
         if ((stages & kGjk) && (rc = launch_gjk_generic<T>(src, num_pairs, (int)pool.max_nv, d_simp, d_dist))) break;
-        if ((stages & kEpa) && (rc = launch_epa<T>(src, num_pairs, d_simp, d_dist, d_nrm))) break;
+        if ((stages & kEpa) && (rc = launch_epa<T>(src, num_pairs, (int)pool.max_nv, d_simp, d_dist, d_nrm))) break;
       }
     }
     if ((e = cudaMemcpyAsync(simplices, d_simp, np * sizeof(SimplexT<T>), cudaMemcpyDeviceToHost, t_stream)) != cudaSuccess) { rc = fail("D2H simplices", e); break; }
@@ -1523,7 +1541,12 @@ long long ogjk_launch_count(int reset) {
                                     REAL* d_distances, REAL* d_contact_normals) {                                     \
     if (n <= 0) return 0;                                                                                              \
     DescSource<REAL> src{(const PolytopeT<REAL>*)d_bd1, (const PolytopeT<REAL>*)d_bd2};                                \
-    return launch_epa<REAL>(src, n, (SimplexT<REAL>*)d_simplices, d_distances, d_contact_normals);                     \
+    /* vertex-count hint: selects lanes per pair only (any count is handled correctly by every kernel) */             \
+    PoolInfo p1, p2;                                                                                                   \
+    int nv = 0;                                                                                                        \
+    if (lookup_pool(d_bd1, &p1) && lookup_pool(d_bd2, &p2)) nv = p1.max_nv > p2.max_nv ? p1.max_nv : p2.max_nv;        \
+    else if (int rc = peek_numpoints<REAL>((const PolytopeT<REAL>*)d_bd1, &nv)) return rc;                             \
+    return launch_epa<REAL>(src, n, nv, (SimplexT<REAL>*)d_simplices, d_distances, d_contact_normals);                 \
   }                                                                                                                    \
   int ogjk_##P##_copy_results_from_device(int n, const void* d_simplices, const REAL* d_distances, void* simplices,   \
                                           REAL* distances) {                                                          \
@@ -1655,7 +1678,7 @@ long long ogjk_launch_count(int reset) {
     if (!rc) rc = launch_gjk_generic<REAL>(src, num_pairs, nv, (SimplexT<REAL>*)d_simplices, d_distances);             \
     t_sync = sync_saved;                                                                                               \
     if (!rc) rc = stage_mark(1);                                                                                       \
-    if (!rc) rc = launch_epa<REAL>(src, num_pairs, (SimplexT<REAL>*)d_simplices, d_distances, d_contact_normals);      \
+    if (!rc) rc = launch_epa<REAL>(src, num_pairs, nv, (SimplexT<REAL>*)d_simplices, d_distances, d_contact_normals);  \
     if (!rc) rc = stage_mark(2);                                                                                       \
     return rc;                                                                                                         \
   }                                                                                                                    \
@@ -1663,7 +1686,11 @@ long long ogjk_launch_count(int reset) {
                                             void* d_simplices, REAL* d_distances, REAL* d_contact_normals) {          \
     if (num_pairs <= 0) return 0;                                                                                      \
     IndexedSource<REAL> src{(const PolytopeT<REAL>*)d_polytopes, (const CollisionPair*)d_pairs};                       \
-    return launch_epa<REAL>(src, num_pairs, (SimplexT<REAL>*)d_simplices, d_distances, d_contact_normals);             \
+    PoolInfo info;                                                                                                     \
+    int nv = 0;                                                                                                        \
+    if (lookup_pool(d_polytopes, &info)) nv = info.max_nv;                                                             \
+    else if (int rc = peek_numpoints<REAL>((const PolytopeT<REAL>*)d_polytopes, &nv)) return rc;                       \
+    return launch_epa<REAL>(src, num_pairs, nv, (SimplexT<REAL>*)d_simplices, d_distances, d_contact_normals);         \
   }                                                                                                                    \
   int ogjk_##P##_compute_epa_indexed(int num_polytopes, int num_pairs, const void* polytopes, const void* pairs,      \
                                      void* simplices, REAL* distances, REAL* contact_normals) {                       \
@@ -1731,7 +1758,8 @@ long long ogjk_launch_count(int reset) {
     if (n <= 0) return 0;                                                                                              \
     if (nverts1 < 1 || nverts2 < 1) return fail_msg("polytope with no vertices");                                      \
     UniformSource<REAL> src{d_coord1, d_coord2, nverts1, nverts2};                                                     \
-    return launch_epa<REAL>(src, n, (SimplexT<REAL>*)d_simplices, d_distances, d_contact_normals);                     \
+    return launch_epa<REAL>(src, n, nverts1 > nverts2 ? nverts1 : nverts2, (SimplexT<REAL>*)d_simplices, d_distances,  \
+                            d_contact_normals);                                                                        \
   }
 
 OGJK_DEFINE_API(f32, float)

@@ -106,17 +106,21 @@ def test_grid_cubes_and_spheres(pkg, oracle_mod, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("nverts,spread", [(32, 1.0), (64, 2.0), (200, 1.5), (8, 0.5)])
-def test_group_kernel_matches_oracle(pkg, oracle_mod, dtype, nverts, spread):
-    """the opt-in sub-warp group EPA kernel (OGJK_EPA_KERNEL=group, epa_group.cuh); needs >= 8192 pairs to be taken"""
+@pytest.mark.parametrize("kernel", ["warp", "group", "small4", "small8"])
+@pytest.mark.parametrize("nverts,spread", [(32, 1.0), (64, 2.0), (200, 1.5), (8, 0.5), (16, 0.3)])
+def test_epa_kernel_families_match_oracle(pkg, oracle_mod, dtype, kernel, nverts, spread):
+    """every EPA kernel family forced through OGJK_EPA_KERNEL (needs >= 8192 pairs to leave the tiny-batch kernel):
+    warp per pair; sub-warp group with the full-size work area; sub-warp groups of 4 / 8 lanes with the SMALL work
+    area + overflow pass -- deep overlaps (spread 0.3 .. 1) send the long-tailed pairs through the overflow queue,
+    200-vertex bodies run the uncached support path"""
     import os
-    n = 12000 if nverts <= 64 else 9000
+    n = 30000 if nverts <= 64 else 9000
     a, b = pkg.workloads.random_pairs(n, nverts, spread, seed=123, dtype=dtype)
     eng = pkg.Engine(dtype)
     bd1, _k1 = pkg.make_polytopes(a)
     bd2, _k2 = pkg.make_polytopes(b)
     saved = os.environ.get("OGJK_EPA_KERNEL")
-    os.environ["OGJK_EPA_KERNEL"] = "group"
+    os.environ["OGJK_EPA_KERNEL"] = kernel
     try:
         got = eng.compute_gjk_epa(bd1, bd2)
     finally:
@@ -124,4 +128,15 @@ def test_group_kernel_matches_oracle(pkg, oracle_mod, dtype, nverts, spread):
             os.environ.pop("OGJK_EPA_KERNEL", None)
         else:
             os.environ["OGJK_EPA_KERNEL"] = saved
-    _compare(dtype, got, _oracle_gjk_epa(oracle_mod, dtype, a, b))
+    orc = oracle_mod.Oracle("port", dtype)
+    s, d = orc.gjk(a, b, nthreads=8)
+    _compare(dtype, got, orc.epa(a, b, s, d, nthreads=8))
+
+
+def test_small_work_area_overflow_is_exercised(pkg, oracle_mod):
+    """the workload above really has pairs beyond the small work area's 24 iterations (so the overflow pass ran)"""
+    a, b = pkg.workloads.random_pairs(30000, 32, 1.0, seed=123, dtype=np.float32)
+    orc = oracle_mod.Oracle("port", np.float32)
+    s, d = orc.gjk(a, b, nthreads=8)
+    _s, _d, _n, it = orc.epa(a, b, s, d, nthreads=8, want_iters=True)
+    assert (it > 26).sum() >= 3
