@@ -300,7 +300,18 @@ int ws_compute_warps(int nv1, int nv2, int esize) {
   int lp;
   return ws_config(nv1, nv2, &lp, esize);
 }
-template <typename T, int CW, int LP>
+// scanner warps (gjk_slots.cuh, SC = 1): fp32, one owner lane per pair, the mailboxes must fit beside the slots.
+// Development override OGJK_WS_SC=0|1.
+template <typename T>
+bool ws_use_scanners(int cw, int lp, int nv1, int nv2) {
+  if (sizeof(T) != 4 || lp != 1 || (cw != 4 && cw != 2)) return false;
+  const char* e = getenv("OGJK_WS_SC");
+  if (e && atoi(e) == 0) return false;
+  const int nslots = cw * 32;
+  return ws_fixed_bytes(nslots, 4, 1) + (size_t)nslots * slot_bytes(nv1, nv2, 4) + kSlotPadBytes <= 227u * 1024u;
+}
+
+template <typename T, int CW, int LP, int SC>
 int launch_gjk_slots_ws_cw(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist, T* nrm,
                            int* queue, int* count, const CollisionPair* pairs) {
   const uint16_t* utab = nullptr;
@@ -309,12 +320,12 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const T* c1, int nv2, const T* c2, Si
   if (int rc = ticket_buffer(&ticket)) return rc;
   constexpr int nslots = CW * 32 / LP;
   constexpr int es = (int)sizeof(T);
-  const size_t smem = (size_t)ws_fixed_bytes(nslots, es) + kSlotPadBytes + (size_t)nslots * ws_slot_layout(nv1, nv2, LP, es).stride;
-  constexpr int threads = (CW + 2) * 32;
-  constexpr bool eq_ok = LP == 1 && es == 4;  // the interleaved two-body scan exists for fp32 only
-  auto kern = pairs ? gjk_slots_ws_kernel<T, CW, LP, eq_ok, true>  // one pool: equal vertex counts by construction
-                    : (eq_ok && nv1 == nv2) ? gjk_slots_ws_kernel<T, CW, LP, eq_ok, false>
-                                            : gjk_slots_ws_kernel<T, CW, LP, false, false>;
+  const size_t smem = (size_t)ws_fixed_bytes(nslots, es, SC) + kSlotPadBytes + (size_t)nslots * ws_slot_layout(nv1, nv2, LP, es).stride;
+  constexpr int threads = (CW + 2 + 2 * CW * SC) * 32;
+  constexpr bool eq_ok = LP == 1 && es == 4 && SC == 0;  // the interleaved two-body scan exists for fp32 only
+  auto kern = pairs ? gjk_slots_ws_kernel<T, CW, LP, eq_ok, true, SC>  // one pool: equal vertex counts by construction
+                    : (eq_ok && nv1 == nv2) ? gjk_slots_ws_kernel<T, CW, LP, eq_ok, false, SC>
+                                            : gjk_slots_ws_kernel<T, CW, LP, false, false, SC>;
   long long grid = 0;
   if (int rc = persistent_grid(kern, threads, smem, &grid)) return rc;
   const long long need = ((long long)n + nslots - 1) / nslots;
@@ -329,13 +340,17 @@ int launch_gjk_slots_ws(int n, int nv1, const T* c1, int nv2, const T* c2, Simpl
                         int* queue, int* count, const CollisionPair* pairs = nullptr) {
   int lp = 1;
   const int cw = ws_config(nv1, nv2, &lp, (int)sizeof(T));
-  if (cw == 8 && lp == 1) return launch_gjk_slots_ws_cw<T, 8, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  if (cw == 8 && lp == 1) return launch_gjk_slots_ws_cw<T, 8, 1, 0>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
   if constexpr (sizeof(T) == 4) {
     if (cw == 8 && lp == 2)
-      return launch_gjk_slots_ws_cw<T, 8, 2>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+      return launch_gjk_slots_ws_cw<T, 8, 2, 0>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+    if (ws_use_scanners<T>(cw, lp, nv1, nv2)) {
+      if (cw == 4) return launch_gjk_slots_ws_cw<T, 4, 1, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+      return launch_gjk_slots_ws_cw<T, 2, 1, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+    }
   }
-  if (cw == 4) return launch_gjk_slots_ws_cw<T, 4, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
-  if (cw == 2) return launch_gjk_slots_ws_cw<T, 2, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  if (cw == 4) return launch_gjk_slots_ws_cw<T, 4, 1, 0>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  if (cw == 2) return launch_gjk_slots_ws_cw<T, 2, 1, 0>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
   return 1;
 }
 
@@ -447,9 +462,11 @@ int launch_epa_group(const Source& src, int n, SimplexT<T>* d_simplices, T* d_di
   return launch_epa_warp_queue<T, Source>(src, n, d_simplices, d_distances, d_normals, q.overflow, q.counters + 2, sms);
 }
 
-// Persistent EPA over a device-side queue of colliding pairs.  Default: the sub-warp group kernel with the small work
-// area -- G = 4 lanes per pair for bodies of up to 32 vertices, G = 8 up to 64 -- followed by the overflow pass; larger
-// bodies (the support scan dominates) and OGJK_EPA_KERNEL=warp take one warp per pair.  Development overrides:
+// Persistent EPA over a device-side queue of colliding pairs.  Default (measured on B200, profiles/r2b_ab_epa.txt):
+// bodies of up to 32 vertices take the sub-warp group kernel with the small work area, G = 4 lanes per pair, followed
+// by the overflow pass -- config 3: 6.29 ms against 7.66 ms per Mi pairs for one warp per pair, config 5: 11.4
+// against 14.1 ms per 4 M pairs; larger bodies (the support scan grows, the bookkeeping does not) take one warp per
+// pair -- 64 vertices: 3.43 ms against 3.56 (G = 8) and 4.53 (G = 4) per 512 Ki deep pairs.  Development overrides:
 // OGJK_EPA_KERNEL=warp|group (group = full-size work area, 8 lanes)|small4|small8.
 template <typename T, typename Source>
 int launch_epa_queue(const Source& src, int n, int nv_hint, SimplexT<T>* d_simplices, T* d_distances, T* d_normals,
@@ -458,7 +475,7 @@ int launch_epa_queue(const Source& src, int n, int nv_hint, SimplexT<T>* d_simpl
   OGJK_CK(cudaGetDevice(&dev));
   OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const char* e = getenv("OGJK_EPA_KERNEL");
-  int mode = nv_hint <= 32 ? 4 : nv_hint <= 64 ? 8 : 0;  // 0 warp per pair, 4 / 8 small work area, 1 full-size group
+  int mode = nv_hint <= 32 ? 4 : 0;  // 0 warp per pair, 4 / 8 small work area with that many lanes, 1 full-size group
   if (e) mode = !strcmp(e, "warp") ? 0 : !strcmp(e, "group") ? 1 : !strcmp(e, "small4") ? 4 : !strcmp(e, "small8") ? 8 : mode;
   constexpr int minb = sizeof(T) == 4 ? 16 : 8;
   if (mode == 4) {
