@@ -789,29 +789,21 @@ gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, 
         awaiting = true;
       };
       uint32_t cur_par = 0;  // parity of the barrier phase that delivered the pair this lane is working on
+      // One trip = [wait until the results of ALL requests in flight are in] -> merge, exit tests, sub-algorithm step,
+      // retire -> take refilled slots -> publish the next requests of all running lanes in ONE burst.  The burst is a
+      // single store instruction, so the scanner warps of these 32 slots see all of a trip's requests at once and
+      // scan them together; answering requests as they trickle in made both sides run at ~9 active lanes and doubled
+      // the instruction count (profiles/r2c_gjk_slots_ws_scanners_cfg2.txt).
       for (;;) {
-        if (state == kWait) {
-          if (mbar_test_wait(bar, parity)) {
-            cur_par = parity;
-            parity ^= 1u;
-            pair = ld_vol(&pair_of[cslot]);
-            gjk_init(g, mk<T>(s1[0], s1[1], s1[2]), mk<T>(s2[0], s2[1], s2[2]));
-            state = kRun;
-            publish(cur_par);
-          } else if (ld_vol(&ctrl[cslot]) == kSlotExit) {
-            st_vol64(&req[2 * cslot + 1], (u64)kSeqExit << 32);  // tell this slot's two scanner threads
-            state = kExit;
-          }
-        }
-        if (__all_sync(0xffffffffu, state == kExit)) break;
         bool got = false;
         u64 r1 = 0, r2 = 0;
-        if (state == kRun && awaiting) {
+        if (awaiting) {
+          const unsigned want = seq | (cur_par << 15);
           r1 = ld_vol64(&res[2 * cslot]);
           r2 = ld_vol64(&res[2 * cslot + 1]);
-          got = (unsigned)(r1 >> 32 & 0xffffu) == (seq | (cur_par << 15)) && (unsigned)(r2 >> 32 & 0xffffu) == (seq | (cur_par << 15));
+          got = ((unsigned)(r1 >> 32) & 0xffffu) == want && ((unsigned)(r2 >> 32) & 0xffffu) == want;
         }
-        if (!__any_sync(0xffffffffu, got)) {
+        if (!__all_sync(0xffffffffu, !awaiting || got)) {
           __nanosleep(20);
           continue;
         }
@@ -835,9 +827,26 @@ gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, 
           }
           finished = gjk_converged_u(g);
           if (!finished) finished = gjk_substep_u(g, utab);
-          if (!finished) publish(cur_par);
         }
-        retire(finished);
+        retire(finished);  // finished lanes: state = kWait
+        bool fresh = false;
+        if (state == kWait) {
+          if (mbar_test_wait(bar, parity)) {
+            cur_par = parity;
+            parity ^= 1u;
+            pair = ld_vol(&pair_of[cslot]);
+            gjk_init(g, mk<T>(s1[0], s1[1], s1[2]), mk<T>(s2[0], s2[1], s2[2]));
+            state = kRun;
+            fresh = true;
+          } else if (ld_vol(&ctrl[cslot]) == kSlotExit) {
+            st_vol64(&req[2 * cslot + 1], (u64)kSeqExit << 32);  // tell this slot's two scanner threads
+            state = kExit;
+          }
+        }
+        if (__all_sync(0xffffffffu, state == kExit)) break;
+        const bool ask = state == kRun && (fresh || (got && !finished));
+        if (ask) publish(cur_par);
+        if (!__any_sync(0xffffffffu, ask || got)) __nanosleep(40);  // nothing to do: every slot is waiting for its refill
       }
     } else {
     bool need_sub = false;  // this lane passed the pre-tests last trip and owes the sub-algorithm step

@@ -134,6 +134,13 @@ struct LaunchCfg {
   int grid_per_device;  // SMs x resident CTAs per SM
 };
 thread_local std::vector<LaunchCfg> t_cfgs;
+struct SmemAttr {
+  int dev;
+  const void* fn;
+  size_t bytes;  // dynamic shared-memory opt-in currently set for this kernel on this device
+};
+std::mutex g_attr_mutex;
+std::vector<SmemAttr> g_attrs;
 template <typename Kernel>
 int persistent_grid(Kernel kern, int threads, size_t smem, long long* grid) {
   int dev = 0;
@@ -145,7 +152,22 @@ int persistent_grid(Kernel kern, int threads, size_t smem, long long* grid) {
       return 0;
     }
   int sms = 0, per_sm = 0;
-  if (smem > 48u * 1024u) OGJK_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the opt-in limit is one attribute per kernel: raise it, never lower it -- another shape of the same kernel may
+  // already be cached here with a larger request and would otherwise fail to launch later
+  if (smem > 48u * 1024u) {
+    std::lock_guard<std::mutex> lock(g_attr_mutex);  // process-wide: the attribute belongs to (device, kernel)
+    SmemAttr* slot = nullptr;
+    for (SmemAttr& a : g_attrs)
+      if (a.dev == dev && a.fn == fn) slot = &a;
+    if (!slot) {
+      g_attrs.push_back(SmemAttr{dev, fn, 0});
+      slot = &g_attrs.back();
+    }
+    if (smem > slot->bytes) {
+      OGJK_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      slot->bytes = smem;
+    }
+  }
   OGJK_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   OGJK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) return fail_msg("persistent kernel does not fit on this device");

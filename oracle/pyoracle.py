@@ -185,3 +185,81 @@ class RefGpu:
         if rc != 0:
             raise RuntimeError(f"reference GPU library failed: cudaError {rc}")
         return simp, dist, nrm, float(ms[0]), float(ms[1])
+
+
+class RefVis:
+    """The reference visualiser's own kernels either side of the hot path (broad phase, world transform, contact
+    response, descriptor upkeep), compiled unmodified by oracle/build_ref_vis.sh.  Needs a GPU."""
+
+    PATH = os.path.join(_HERE, "_ref_gpu", "libogjk_refvis_f32.so")
+
+    @classmethod
+    def available(cls) -> bool:
+        return os.path.exists(cls.PATH)
+
+    def __init__(self):
+        if not self.available():
+            raise FileNotFoundError(f"{self.PATH} missing: run oracle/build_ref_vis.sh where /root/reference exists")
+        self.lib = ctypes.CDLL(self.PATH)
+        self.lib.ogjk_refvis_broadphase.restype = ctypes.c_long
+
+    def broadphase(self, pos_radius, cell_size, boundary, grid_size, max_pairs):
+        """-> int32 [m, 2] in the reference's emission order (grouped by idx1; order inside a group follows the
+        atomic slot order of insert_objects_kernel, i.e. is not deterministic)"""
+        p = np.ascontiguousarray(pos_radius, np.float32)
+        out = np.zeros((max_pairs, 2), np.int32)
+        total = self.lib.ogjk_refvis_broadphase(ctypes.c_int(p.shape[0]), Oracle._p(p), ctypes.c_float(cell_size),
+                                                ctypes.c_float(boundary), ctypes.c_int(grid_size), Oracle._p(out),
+                                                ctypes.c_int(max_pairs))
+        if total < 0:
+            raise RuntimeError("reference broad phase failed" if total == -1 else
+                               "reference broad phase dropped objects (more than 512 per cell)")
+        return out[: min(total, max_pairs)], int(total)
+
+    def transform(self, positions, quats, scales, verts_local, offsets, counts, sub_body):
+        pos = np.ascontiguousarray(positions, np.float32)
+        q = np.ascontiguousarray(quats, np.float32)
+        sc = np.ascontiguousarray(scales, np.float32)
+        lv = np.ascontiguousarray(verts_local, np.float32).reshape(-1, 3)
+        off = np.ascontiguousarray(offsets, np.int32)
+        cnt = np.ascontiguousarray(counts, np.int32)
+        sb = np.ascontiguousarray(sub_body, np.int32)
+        out = np.zeros_like(lv)
+        rc = self.lib.ogjk_refvis_transform(ctypes.c_int(len(off)), ctypes.c_int(pos.shape[0]), ctypes.c_int(lv.shape[0]),
+                                            Oracle._p(pos), Oracle._p(q), Oracle._p(sc), Oracle._p(lv), Oracle._p(out),
+                                            Oracle._p(off), Oracle._p(cnt), Oracle._p(sb))
+        if rc:
+            raise RuntimeError(f"reference transform failed: cudaError {rc}")
+        return out
+
+    def response(self, pairs, distances, simplices, normals, sub_mesh_body, positions, vel_ping, ang_ping, quats,
+                 inv_inertia, epsilon):
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        dist = np.ascontiguousarray(distances, np.float32)
+        simp = np.ascontiguousarray(simplices)
+        nrm = np.ascontiguousarray(normals, np.float32)
+        smb = np.ascontiguousarray(sub_mesh_body, np.int32)
+        pos = np.array(positions, np.float32, copy=True)
+        vp = np.ascontiguousarray(vel_ping, np.float32)
+        ap = np.ascontiguousarray(ang_ping, np.float32)
+        q = np.ascontiguousarray(quats, np.float32)
+        ii = np.ascontiguousarray(inv_inertia, np.float32)
+        vq, aq = np.zeros_like(vp), np.zeros_like(ap)
+        rc = self.lib.ogjk_refvis_response(ctypes.c_int(pairs.shape[0]), Oracle._p(pairs), Oracle._p(dist), Oracle._p(simp),
+                                           Oracle._p(nrm), Oracle._p(smb), ctypes.c_int(len(smb)), ctypes.c_int(pos.shape[0]),
+                                           Oracle._p(pos), Oracle._p(vp), Oracle._p(vq), Oracle._p(ap), Oracle._p(aq),
+                                           Oracle._p(q), Oracle._p(ii), ctypes.c_float(epsilon))
+        if rc:
+            raise RuntimeError(f"reference response failed: cudaError {rc}")
+        return pos, vq, aq
+
+    def init_polytopes(self, offsets, counts):
+        off = np.ascontiguousarray(offsets, np.int32)
+        cnt = np.ascontiguousarray(counts, np.int32)
+        npts = np.zeros(len(off), np.int32)
+        coff = np.zeros(len(off), np.int64)
+        rc = self.lib.ogjk_refvis_init_polytopes(ctypes.c_int(len(off)), Oracle._p(off), Oracle._p(cnt), Oracle._p(npts),
+                                                 Oracle._p(coff))
+        if rc:
+            raise RuntimeError(f"reference init_polytopes failed: cudaError {rc}")
+        return npts, coff
