@@ -8,15 +8,18 @@
 // fx*fx + fy*fy + fz*fz < (ri + rj)*(ri + rj) in fp32; pairs come out grouped by i in ascending order, each group at
 // the exclusive prefix sum of the per-object counts, and writes beyond `max_pairs` are dropped.
 // What differs is the machine mapping:
-//   * cell lists are compact (histogram -> exclusive scan -> fill) instead of a fixed 512 ids per cell: 80 KB instead
-//     of 55 MB for the 30^3 grid, and no silent loss of the objects beyond 512 in a crowded cell;
+//   * cell lists are compact (histogram -> exclusive scan -> stable sort of the object ids by cell) instead of a fixed
+//     512 ids per cell: 80 KB instead of 55 MB for the 30^3 grid, and no silent loss of the objects beyond 512 in a
+//     crowded cell;
 //   * counting and generation use one WARP per object: the lanes stride over the candidates of the 27 cells, counts
 //     are reduced with REDUX, pairs are written through ballot/popc compaction (the reference walks ~1600 candidates
 //     per thread serially with 20 000 threads in flight for BASELINE config 5);
 //   * the arithmetic of the overlap test is written with explicitly rounded operations (the reference's build lets
 //     nvcc contract it), so that the pair SET is reproducible and equals the numpy oracle bit for bit.
-// The order of the pairs inside one object's group follows the cell lists, which are filled with atomics -- as in the
-// reference it is not deterministic; consumers (GJK/EPA) do not depend on it.
+// The order of the pairs inside one object's group follows the cell lists.  The reference fills those with atomics, so
+// its order changes from run to run; here every cell list is in ascending object id (the ids are sorted by cell with a
+// stable radix sort -- cub::DeviceRadixSort, a library call off the hot path), so the whole pair list, and with it
+// the pair-ordered contact response downstream, is reproducible run to run.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -47,12 +50,13 @@ OGJK_D bool bp_overlap(const float4& a, const float4& b) {
 // cell of every object + histogram
 __global__ void __launch_bounds__(256)
 bp_histogram_kernel(const float4* __restrict__ pos, int n, float cell_size, float boundary, int grid_size,
-                    int* __restrict__ obj_cell, int* __restrict__ cell_count) {
+                    int* __restrict__ obj_cell, int* __restrict__ obj_id, int* __restrict__ cell_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int cx, cy, cz;
   const int c = bp_cell_of(pos[i], boundary, cell_size, grid_size, cx, cy, cz);
   obj_cell[i] = c;
+  obj_id[i] = i;
   atomicAdd(&cell_count[c], 1);
 }
 
@@ -105,16 +109,6 @@ bp_exclusive_scan_kernel(const int* __restrict__ in, int* __restrict__ out, int 
     __syncthreads();
   }
   if (tid == 0) out[n] = carry_s;
-}
-
-// compact cell lists: objects of cell c occupy cell_objs[cell_start[c] .. cell_start[c + 1])
-__global__ void __launch_bounds__(256)
-bp_fill_kernel(const int* __restrict__ obj_cell, int n, const int* __restrict__ cell_start, int* __restrict__ cursor,
-               int* __restrict__ cell_objs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int c = obj_cell[i];
-  cell_objs[cell_start[c] + atomicAdd(&cursor[c], 1)] = i;
 }
 
 // One warp per object.  kWrite = false: pair_counts[obj] = number of partners; kWrite = true: the pairs themselves at

@@ -511,50 +511,9 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
       // order (EPA.c:761-775)
       int base_rank = 0;
       bool any_degenerate = false;
-      // Small work area (<= 48 edges per pair): the uniqueness test is done by the WHOLE warp for one group after the
-      // other -- lane l takes edge l of that group's list, match.any on the undirected key counts its occurrences --
-      // instead of every lane comparing its edge with all the others (15 % of the kernel's instructions,
-      // profiles/r2c_epa_small4_cfg3.txt).  keepw = this group's horizon bits, edge e -> bit e.
-      uint32_t keepw0 = 0u, keepw1 = 0u;
-      if constexpr (WT::kSmall && G < 32) {
-#pragma unroll 1
-        for (int gi = 0; gi < 32 / G; ++gi) {
-          const int ne = __shfl_sync(0xffffffffu, nedge, gi * G);  // warp-uniform
-          if (ne == 0) continue;
-          const WT& Wg = work[gi];
-          const bool mine = (wlane / G) == gi;
-          if (ne <= 32) {
-            uint32_t canon = 0xffff0000u | (uint32_t)wlane;  // idle lanes: unique dummies
-            if (wlane < ne) {
-              const uint32_t k = Wg.edge[wlane];
-              const uint32_t x = k >> 8, y = k & 0xff;
-              canon = x < y ? k : ((y << 8) | x);
-            }
-            const unsigned same = __match_any_sync(0xffffffffu, canon);
-            const unsigned km = __ballot_sync(0xffffffffu, wlane < ne && __popc(same) == 1);
-            if (mine) keepw0 = km;
-          } else {  // 33..48 edges (rare): two rounds, each lane compares its edge with the whole list
-#pragma unroll 1
-            for (int r = 0; r < 2; ++r) {
-              const int e = 32 * r + wlane;
-              bool uniq = e < ne;
-              if (uniq) {
-                const uint32_t k = Wg.edge[e];
-                const uint32_t rv = ((k & 0xff) << 8) | (k >> 8);
-                for (int x = 0; x < ne; ++x) {
-                  const uint32_t other = Wg.edge[x];
-                  if (x != e && (other == k || other == rv)) uniq = false;
-                }
-              }
-              const unsigned km = __ballot_sync(0xffffffffu, uniq);
-              if (mine) {
-                if (r == 0) keepw0 = km;
-                else keepw1 = km;
-              }
-            }
-          }
-        }
-      }
+      // (Measured and dropped: letting the whole warp test one group's edge list after the other with match.any on the
+      // undirected key instead of this all-pairs loop -- config 3 went from 6.29 to 7.27 ms per Mi pairs,
+      // profiles/r2d_ab_epa.txt: eight MATCH + VOTE + SHFL rounds per expansion cost more than the loop they replace.)
       for (int e0 = 0; e0 < nedgew; e0 += G) {
         const int e = e0 + g.lane;
         bool keep = e < nedge;
@@ -563,14 +522,10 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
           key = W.edge[e];
           rev = ((key & 0xff) << 8) | (key >> 8);
         }
-        if constexpr (WT::kSmall && G < 32) {
-          keep = keep && (((e < 32 ? keepw0 : keepw1) >> (e & 31)) & 1u);
-        } else {
-          for (int x = 0; x < nedgew; ++x) {
-            if (x < nedge) {
-              const uint32_t other = W.edge[x];
-              if (x != e && (other == key || other == rev)) keep = false;
-            }
+        for (int x = 0; x < nedgew; ++x) {
+          if (x < nedge) {
+            const uint32_t other = W.edge[x];
+            if (x != e && (other == key || other == rev)) keep = false;
           }
         }
         const unsigned keepm = gw.ballot(keep);

@@ -1271,24 +1271,34 @@ int broadphase_pairs(int n, const float4* d_pos, float cell_size, float boundary
   if (!d_pos || (!d_pairs && max_pairs > 0)) return fail_msg("null argument");
   if (!(cell_size > 0.0f) || grid_size < 1 || grid_size > 512) return fail_msg("bad grid (cell_size > 0, 1 <= grid_size <= 512)");
   const size_t cells = (size_t)grid_size * grid_size * grid_size;
-  // obj_cell[n] | cell_count[cells] | cursor[cells] | cell_start[cells + 1] | cell_objs[n] | pair_counts[n] | pair_offsets[n + 1]
-  const size_t ints = 3 * (size_t)n + 3 * cells + (size_t)n + 2;
+  // obj_cell[n] | cell_count[cells] | cell_start[cells + 1] | cell_objs[n] | pair_counts[n] | pair_offsets[n + 1] |
+  // obj_id[n] | sorted keys[n] | radix-sort temporary
+  int key_bits = 1;
+  while ((1ll << key_bits) < (long long)cells) ++key_bits;
+  size_t sort_bytes = 0;
+  OGJK_CK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr,
+                                          (int*)nullptr, n, 0, key_bits, t_stream));
+  const size_t ints = 6 * (size_t)n + 2 * cells + 2 + (sort_bytes + 3) / 4 + 4;
   StreamScratch* ss = nullptr;
   if (int rc = stream_scratch(&ss)) return rc;
   int* obj_cell = nullptr;
   if (int rc = scratch_grow(ss->bp, ints, &obj_cell)) return rc;
   int* cell_count = obj_cell + n;
-  int* cursor = cell_count + cells;
-  int* cell_start = cursor + cells;
+  int* cell_start = cell_count + cells;
   int* cell_objs = cell_start + cells + 1;
   int* pair_counts = cell_objs + n;
   int* pair_offsets = pair_counts + n;
-  OGJK_CK(cudaMemsetAsync(cell_count, 0, 2 * cells * sizeof(int), t_stream));  // counts + cursors
+  int* obj_id = pair_offsets + n + 1;
+  int* keys_sorted = obj_id + n;
+  void* sort_tmp = (void*)(((uintptr_t)(keys_sorted + n) + 15u) & ~(uintptr_t)15u);
+  OGJK_CK(cudaMemsetAsync(cell_count, 0, cells * sizeof(int), t_stream));
   const unsigned tb = (unsigned)((n + 255) / 256);
   const unsigned wb = (unsigned)(((long long)n * 32 + 255) / 256);
-  bp_histogram_kernel<<<tb, 256, 0, t_stream>>>(d_pos, n, cell_size, boundary, grid_size, obj_cell, cell_count);
+  bp_histogram_kernel<<<tb, 256, 0, t_stream>>>(d_pos, n, cell_size, boundary, grid_size, obj_cell, obj_id, cell_count);
   bp_exclusive_scan_kernel<<<1, 1024, 0, t_stream>>>(cell_count, cell_start, (int)cells);
-  bp_fill_kernel<<<tb, 256, 0, t_stream>>>(obj_cell, n, cell_start, cursor, cell_objs);
+  // cell lists in ascending object id: stable sort of the ids by cell (deterministic, unlike an atomic cursor fill)
+  OGJK_CK(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, obj_cell, keys_sorted, obj_id, cell_objs, n, 0, key_bits,
+                                          t_stream));
   bp_pairs_kernel<false><<<wb, 256, 0, t_stream>>>(d_pos, n, cell_size, boundary, grid_size, cell_start, cell_objs,
                                                    pair_counts, nullptr, nullptr, 0);
   bp_exclusive_scan_kernel<<<1, 1024, 0, t_stream>>>(pair_counts, pair_offsets, n);

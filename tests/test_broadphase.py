@@ -65,9 +65,17 @@ def test_device_broadphase_matches_oracle(pkg, n, cell, boundary, grid):
     got = d_pairs.cpu().numpy()[:total]
     assert np.all(got[:, 0] < got[:, 1])
     assert np.all(np.diff(got[:, 0]) >= 0), "pairs must be grouped by idx1 in ascending order"
+    raw = got.copy()
     got = got[np.lexsort((got[:, 1], got[:, 0]))]
     assert np.array_equal(got, want)
     assert np.all(d_pairs.cpu().numpy()[total:] == -1)
+    # reproducible ORDER too (cell lists are sorted by object id, not filled through an atomic cursor): the contact
+    # response downstream folds contributions in pair order
+    for _ in range(2):
+        d_again = torch.full((cap, 2), -1, dtype=torch.int32, device="cuda")
+        assert eng.broadphase_pairs_device(n, d_p, cell, boundary, grid, d_again, cap) == total
+        torch.cuda.synchronize()
+        assert np.array_equal(d_again.cpu().numpy()[:total], raw)
     # clamp: a buffer that is too small is filled and nothing is written past it
     small = total // 2
     d_small = torch.full((small + 5, 2), -1, dtype=torch.int32, device="cuda")
