@@ -169,54 +169,6 @@ OGJK_D void support_slot(const float* body, int nv, const V3<float>& d, unsigned
   }
 }
 
-// Scanner-warp form: the maximum and the lowest index attaining it, from -inf, over one body.  The caller applies the
-// "strictly greater than the current support point" rule (openGJK.c:615-639) itself.
-OGJK_D void scan_slot(const float* body, int nv, const V3<float>& d, unsigned zero, float& best_out, int& idx_out) {
-  const ulonglong2* chunk = reinterpret_cast<const ulonglong2*>(body);
-  const DirPack D = make_dir(d, zero);
-  float best = -INFINITY;
-  int bg = 0;
-  const int groups = nv >> 2;
-  const int pairs = groups >> 1;
-  Block4 k0 = load_block(chunk, 0);
-  Block4 k1 = load_block(chunk, 1);
-#pragma unroll 2
-  for (int t = 0; t < pairs; ++t) {
-    const Block4 n0 = load_block(chunk, 2 * t + 2);
-    const Block4 n1 = load_block(chunk, 2 * t + 3);
-    float da[4], db[4];
-    dots4(k0, D, da);
-    dots4(k1, D, db);
-    const float ma = max4(da), mb = max4(db);
-    if (ma > best) {
-      best = ma;
-      bg = 2 * t;
-    }
-    if (mb > best) {
-      best = mb;
-      bg = 2 * t + 1;
-    }
-    k0 = n0;
-    k1 = n1;
-  }
-  if (groups & 1) {
-    float da[4];
-    dots4(k0, D, da);
-    const float ma = max4(da);
-    if (ma > best) {
-      best = ma;
-      bg = groups - 1;
-    }
-  }
-  float dd[4];
-  dots4(load_block(chunk, bg), D, dd);
-  int k = 3;
-  if (dd[2] == best) k = 2;
-  if (dd[1] == best) k = 1;
-  if (dd[0] == best) k = 0;
-  best_out = best;
-  idx_out = 4 * bg + k;
-}
 // Both bodies of a pair in one loop (equal vertex counts): two independent scan streams interleaved, so that the
 // single warp a scheduler has (64+64-vertex slots) finds an independent instruction more often.
 OGJK_D void recover_support(const float* body, const ulonglong2* chunk, int bg, float best, const DirPack& D,
@@ -423,34 +375,6 @@ OGJK_D void support_slots_both(const double* b1, const double* b2, int nv, const
   support_slot(b2, nv, v, zero, sup2, idx2);
 }
 
-OGJK_D void scan_slot(const double* body, int nv, const V3<double>& d, unsigned, double& best_out, int& idx_out) {
-  const double2* chunk = reinterpret_cast<const double2*>(body);
-  double best = -INFINITY;
-  int bg = 0;
-  const int groups = nv >> 2;
-  Block4d k0 = load_block(chunk, 0);
-#pragma unroll 2
-  for (int g = 0; g < groups; ++g) {
-    const Block4d n0 = load_block(chunk, g + 1);
-    double da[4];
-    dots4(k0, d, da);
-    const double ma = max4(da);
-    if (ma > best) {
-      best = ma;
-      bg = g;
-    }
-    k0 = n0;
-  }
-  double dd[4];
-  dots4(load_block(chunk, bg), d, dd);
-  int k = 3;
-  if (dd[2] == best) k = 2;
-  if (dd[1] == best) k = 1;
-  if (dd[0] == best) k = 0;
-  best_out = best;
-  idx_out = 4 * bg + k;
-}
-
 // integers travel through the finisher's records as bit patterns of T
 OGJK_D float rec_from_int(float, unsigned v) { return __uint_as_float(v); }
 OGJK_D double rec_from_int(double, unsigned v) { return __longlong_as_double((long long)v); }
@@ -607,16 +531,13 @@ constexpr int kRecWords = 49;  // odd stride: lanes writing/reading consecutive 
 // record layout (words): 0 pair | 1 n | 2..4 v | 5+5k.. slot k: p.xyz, i1, i2 | 25+6k.. slot k: body-1 xyz, body-2 xyz
 enum : unsigned { kSlotFree = 0u, kSlotBusy = 1u, kSlotExit = 2u };
 
-__host__ __device__ constexpr uint32_t ws_fixed_bytes(int nslots, int esize = 4, int sc = 0) {
+__host__ __device__ constexpr uint32_t ws_fixed_bytes(int nslots, int esize = 4) {
   // mbarriers | table | ctrl | pair_of | ring control (16 B) | ready flags | ring (kRecWords elements of T per record)
-  // | scanner mailboxes (request: 2 x 8 B, results: 2 x 8 B per slot)
   return (uint32_t)nslots * 8u + kSlotTableBytes + (uint32_t)nslots * 4u * 2u + 16u + ring_records(nslots) * 4u +
-         (((uint32_t)ring_records(nslots) * kRecWords * (uint32_t)esize + 15u) & ~15u) + (sc ? (uint32_t)nslots * 32u : 0u);
+         (((uint32_t)ring_records(nslots) * kRecWords * (uint32_t)esize + 15u) & ~15u);
 }
 
 OGJK_D unsigned ld_vol(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
-OGJK_D u64 ld_vol64(const u64* p) { return *reinterpret_cast<const volatile u64*>(p); }
-OGJK_D void st_vol64(u64* p, u64 v) { *reinterpret_cast<volatile u64*>(p) = v; }
 OGJK_D void st_vol(unsigned* p, unsigned v) { *reinterpret_cast<volatile unsigned*>(p) = v; }
 
 template <typename T>
@@ -634,32 +555,16 @@ struct RecordFetch {  // vertex "index" = original simplex slot in bits 30..31 (
 // issue from while the first waits on a dependency.
 // IDX: pairs are gkCollisionPair records into one pool (ticket feed with record prefetch); otherwise pair t is
 // (coord1[t], coord2[t]) and the loader draws plain ticket ranges.
-//
-// SC = 1: SCANNER WARPS (fp32, LP = 1).  With 64+64-vertex slots only CW = 4 compute warps fit an SM -- one per
-// scheduler -- and a trip of such a warp is ~1800 instructions of which ~700 are the two support scans; every stall of
-// that dependent chain is exposed (issue slots 40 % busy, profiles/r2a_gjk_slots_ws_cfg2.txt).  The slot count cannot
-// grow, but the work on a slot can be spread: 2 * CW scanner warps are added, one scanner thread per (slot, body).
-// The owner thread of a slot publishes its search direction in a shared-memory mailbox and goes on with other lanes'
-// work; the two scanner threads of the slot scan one body each (max + lowest index, from -inf, exactly the
-// arithmetic of support_slot) and post (value, index); the owner merges them under the reference's "strictly
-// greater than the current support" rule, runs the exit tests and the sub-algorithm step and publishes the next
-// direction.  No instruction is executed redundantly (unlike LP = 2), each scheduler has three compute-side warps to
-// issue from, and a pair's iteration is [one scan] + [sub-algorithm] long instead of [two scans] + [sub-algorithm].
-// Mailbox words are single 64-bit scalars carrying a 16-bit sequence number (bit 15 = the phase parity of the slot's
-// TMA barrier, which the scanner acquires before touching the slot), so a reader sees a whole message or none.
-template <typename T, int CW, int LP, bool EQ, bool IDX, int SC = 0>
-__global__ void __launch_bounds__((CW + 2 + 2 * CW * SC) * 32)
+template <typename T, int CW, int LP, bool EQ, bool IDX>
+__global__ void __launch_bounds__((CW + 2) * 32)
 gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, int nv1, int nv2,
                     SimplexT<T>* __restrict__ simplices, T* __restrict__ distances, unsigned n,
                     const uint16_t* __restrict__ utab_g, unsigned* __restrict__ ticket, unsigned zero,
                     T* __restrict__ normals, int* __restrict__ epa_queue, int* __restrict__ epa_count,
                     const CollisionPair* __restrict__ pairs, unsigned dense_chunk) {
-  static_assert(SC == 0 || (LP == 1 && sizeof(T) == 4), "scanner warps: fp32, one owner lane per pair");
   constexpr int kCompute = CW * 32;
   constexpr int kSlots = kCompute / LP;
   constexpr int kRingRecords = ring_records(kSlots);
-  constexpr int kThreads = (CW + 2 + 2 * CW * SC) * 32;
-  constexpr unsigned kSeqExit = 0xffffu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const SlotLayout lay = ws_slot_layout(nv1, nv2, LP, (int)sizeof(T));
   const uint32_t sbytes = lay.stride;
@@ -677,25 +582,18 @@ gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, 
   unsigned* ready = reinterpret_cast<unsigned*>(sp);
   sp += kRingRecords * 4;
   T* ring = reinterpret_cast<T*>(sp);
-  sp += ((uint32_t)kRingRecords * kRecWords * (uint32_t)sizeof(T) + 15u) & ~15u;
-  u64* req = reinterpret_cast<u64*>(sp);        // [slot][2]: (v.x, v.y) | (v.z, seq)      (SC only)
-  u64* res = req + 2 * kSlots;                  // [slot][2]: body 1 | body 2: (best, index << 16 | seq)
-  unsigned char* slots = smem_raw + ws_fixed_bytes(kSlots, (int)sizeof(T), SC);
+  unsigned char* slots = smem_raw + ws_fixed_bytes(kSlots, (int)sizeof(T));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bytes1 = (uint32_t)nv1 * 3u * (uint32_t)sizeof(T), bytes2 = (uint32_t)nv2 * 3u * (uint32_t)sizeof(T);
 
-  for (int i = tid; i < kUnifiedSize / 2; i += kThreads)
+  for (int i = tid; i < kUnifiedSize / 2; i += (CW + 2) * 32)
     reinterpret_cast<uint32_t*>(utab)[i] = __ldg(reinterpret_cast<const uint32_t*>(utab_g) + i);
   if (tid < kSlots) {
     mbar_init(smem_addr(&bars[tid]), 1);
     ctrl[tid] = kSlotFree;
     pair_of[tid] = 0;
-    if (SC) {
-      req[2 * tid] = req[2 * tid + 1] = 0ull;
-      res[2 * tid] = res[2 * tid + 1] = 0ull;
-    }
   }
-  for (int i = tid; i < kRingRecords; i += kThreads) ready[i] = 0;
+  for (int i = tid; i < kRingRecords; i += (CW + 2) * 32) ready[i] = 0;
   if (tid < 4) ring_ctl[tid] = 0;
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   fence_proxy_async();
@@ -718,136 +616,6 @@ gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, 
     // the refill overlaps the other lanes' sub-algorithm step.  The arithmetic per pair is the same sequence as in
     // gjk_advance_u.  (Measured: 0.769 against 0.774 ms on config 2 -- the refill, ~2 us from HBM, is still longer
     // than the sub-algorithm step, profiles/r1e_experiments.txt.)
-    auto retire = [&](bool done) {
-      const unsigned fin = __ballot_sync(0xffffffffu, done && half == 0);
-      if (!fin) return;
-      const unsigned cnt = __popc(fin);
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(&ring_ctl[0], cnt);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      while ((int)(base + cnt - ld_vol(&ring_ctl[1])) > kRingRecords) __nanosleep(64);  // ring full: wait for space
-      const unsigned idx = base + __popc(fin & ((1u << (lane & ~(LP - 1))) - 1u));
-      if (done) {
-        T* rec = ring + (size_t)(idx % kRingRecords) * kRecWords;
-        const SV<T>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
-        // all slot reads first, then all record writes: both are shared memory, so the compiler keeps their order
-        // and a load placed after a store would wait out its full latency before the next store can issue
-        T vert[4][6];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (LP == 1 || (k >> 1) == half) {
-            const SV<T>& q = *sv[k];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              vert[k][c] = s1[3 * q.i1 + c];
-              vert[k][3 + c] = s2[3 * q.i2 + c];
-            }
-          }
-        }
-        if (half == 0) {
-          rec[0] = rec_from_int(T(0), pair);
-          rec[1] = rec_from_int(T(0), (unsigned)g.S.n);
-          rec[2] = g.v.x;
-          rec[3] = g.v.y;
-          rec[4] = g.v.z;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (LP == 1 || (k >> 1) == half) {
-            const SV<T>& q = *sv[k];
-            rec[5 + 5 * k + 0] = q.p.x;
-            rec[5 + 5 * k + 1] = q.p.y;
-            rec[5 + 5 * k + 2] = q.p.z;
-            rec[5 + 5 * k + 3] = rec_from_int(T(0), (unsigned)q.i1);
-            rec[5 + 5 * k + 4] = rec_from_int(T(0), (unsigned)q.i2);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) rec[25 + 6 * k + c] = vert[k][c];
-          }
-        }
-        __threadfence_block();  // record + this thread's slot reads before the two flags
-      }
-      __syncwarp();
-      if (done) {
-        if (half == 0) {
-          st_vol(&ready[idx % kRingRecords], idx / kRingRecords + 1u);
-          st_vol(&ctrl[cslot], kSlotFree);
-        }
-        state = kWait;
-      }
-    };
-    if constexpr (SC != 0) {
-      // ---- owner loop with scanner warps: [poll mailbox] -> merge -> exit tests -> sub-algorithm -> [publish] -------
-      unsigned seq = 0;       // sequence number of the request in flight (15 bits, never 0)
-      bool awaiting = false;  // a request is in flight
-      auto publish = [&](uint32_t par) {
-        seq = (seq % 0x7ffeu) + 1u;
-        const u64 lo = (u64)__float_as_uint((float)g.v.x) | ((u64)__float_as_uint((float)g.v.y) << 32);
-        const u64 hi = (u64)__float_as_uint((float)g.v.z) | ((u64)(seq | (par << 15)) << 32);
-        req[2 * cslot] = lo;
-        __threadfence_block();
-        st_vol64(&req[2 * cslot + 1], hi);
-        awaiting = true;
-      };
-      uint32_t cur_par = 0;  // parity of the barrier phase that delivered the pair this lane is working on
-      // One trip = [wait until the results of ALL requests in flight are in] -> merge, exit tests, sub-algorithm step,
-      // retire -> take refilled slots -> publish the next requests of all running lanes in ONE burst.  The burst is a
-      // single store instruction, so the scanner warps of these 32 slots see all of a trip's requests at once and
-      // scan them together; answering requests as they trickle in made both sides run at ~9 active lanes and doubled
-      // the instruction count (profiles/r2c_gjk_slots_ws_scanners_cfg2.txt).
-      for (;;) {
-        bool got = false;
-        u64 r1 = 0, r2 = 0;
-        if (awaiting) {
-          const unsigned want = seq | (cur_par << 15);
-          r1 = ld_vol64(&res[2 * cslot]);
-          r2 = ld_vol64(&res[2 * cslot + 1]);
-          got = ((unsigned)(r1 >> 32) & 0xffffu) == want && ((unsigned)(r2 >> 32) & 0xffffu) == want;
-        }
-        // (no sleep while results are outstanding: __nanosleep's granularity is of the order of the scan itself, and
-        // the hand-over sits on every iteration's critical path -- 1.01 ms against this form, profiles/r2d_*)
-        if (!__all_sync(0xffffffffu, !awaiting || got)) continue;
-        bool finished = false;
-        if (got) {
-          __threadfence_block();
-          awaiting = false;
-          ++g.k;
-          // the reference's support rule (openGJK.c:615-639): only a vertex STRICTLY better than the current support
-          // point replaces it; the scanners returned the lowest index attaining each body's maximum
-          const V3<T> nvv = vneg(g.v);
-          const T b1 = __uint_as_float((unsigned)r1), b2 = __uint_as_float((unsigned)r2);
-          const int i1 = (int)(r1 >> 48), i2 = (int)(r2 >> 48);
-          if (b1 > dot(g.sup1, nvv)) {
-            g.sup1 = mk<T>(s1[3 * i1], s1[3 * i1 + 1], s1[3 * i1 + 2]);
-            g.idx1 = i1;
-          }
-          if (b2 > dot(g.sup2, g.v)) {
-            g.sup2 = mk<T>(s2[3 * i2], s2[3 * i2 + 1], s2[3 * i2 + 2]);
-            g.idx2 = i2;
-          }
-          finished = gjk_converged_u(g);
-          if (!finished) finished = gjk_substep_u(g, utab);
-        }
-        retire(finished);  // finished lanes: state = kWait
-        bool fresh = false;
-        if (state == kWait) {
-          if (mbar_test_wait(bar, parity)) {
-            cur_par = parity;
-            parity ^= 1u;
-            pair = ld_vol(&pair_of[cslot]);
-            gjk_init(g, mk<T>(s1[0], s1[1], s1[2]), mk<T>(s2[0], s2[1], s2[2]));
-            state = kRun;
-            fresh = true;
-          } else if (ld_vol(&ctrl[cslot]) == kSlotExit) {
-            st_vol64(&req[2 * cslot + 1], (u64)kSeqExit << 32);  // tell this slot's two scanner threads
-            state = kExit;
-          }
-        }
-        if (__all_sync(0xffffffffu, state == kExit)) break;
-        const bool ask = state == kRun && (fresh || (got && !finished));
-        if (ask) publish(cur_par);
-        if (!__any_sync(0xffffffffu, ask || got)) __nanosleep(40);  // nothing to do: every slot is waiting for its refill
-      }
-    } else {
     bool need_sub = false;  // this lane passed the pre-tests last trip and owes the sub-algorithm step
     for (;;) {
       bool fin_sub = false;
@@ -903,13 +671,74 @@ gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, 
         finished = gjk_converged_u(g);
         need_sub = !finished;
       }
+      // (Measured and dropped in round 2: SCANNER WARPS -- 2 x CW extra warps, one thread per (slot, body), scanning on
+      // request through shared-memory mailboxes while the slot's owner thread only merges, tests and runs the
+      // sub-algorithm step; bit-exact, 60 % issue utilisation, but 1.01-1.23 ms against 0.77 ms: the two hand-overs per
+      // iteration cost more than the scan they take off the owner's chain -- profiles/r2_experiments.txt, ncu
+      // summaries profiles/r2[c-e]_gjk_slots_ws_scanners_*.txt, code in commits d972fc6..3664304.)
       // (Measured and dropped: a second retire call site in front of the sub-algorithm; pulling upcoming pairs into L2
       // -- cp.async.bulk.prefetch.L2 or per-line prefetch.global.L2 from the loader, any distance; staging buffers
       // behind the slots; extra compute warps with register-resident pairs.  profiles/r1c_gjk_kernels_ab.txt,
       // profiles/r1e_experiments.txt.)
+      auto retire = [&](bool done) {
+        const unsigned fin = __ballot_sync(0xffffffffu, done && half == 0);
+        if (!fin) return;
+        const unsigned cnt = __popc(fin);
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&ring_ctl[0], cnt);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        while ((int)(base + cnt - ld_vol(&ring_ctl[1])) > kRingRecords) __nanosleep(64);  // ring full: wait for space
+        const unsigned idx = base + __popc(fin & ((1u << (lane & ~(LP - 1))) - 1u));
+        if (done) {
+          T* rec = ring + (size_t)(idx % kRingRecords) * kRecWords;
+          const SV<T>* sv[4] = {&g.S.s0, &g.S.s1, &g.S.s2, &g.S.s3};
+          // all slot reads first, then all record writes: both are shared memory, so the compiler keeps their order
+          // and a load placed after a store would wait out its full latency before the next store can issue
+          T vert[4][6];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (LP == 1 || (k >> 1) == half) {
+              const SV<T>& q = *sv[k];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                vert[k][c] = s1[3 * q.i1 + c];
+                vert[k][3 + c] = s2[3 * q.i2 + c];
+              }
+            }
+          }
+          if (half == 0) {
+            rec[0] = rec_from_int(T(0), pair);
+            rec[1] = rec_from_int(T(0), (unsigned)g.S.n);
+            rec[2] = g.v.x;
+            rec[3] = g.v.y;
+            rec[4] = g.v.z;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (LP == 1 || (k >> 1) == half) {
+              const SV<T>& q = *sv[k];
+              rec[5 + 5 * k + 0] = q.p.x;
+              rec[5 + 5 * k + 1] = q.p.y;
+              rec[5 + 5 * k + 2] = q.p.z;
+              rec[5 + 5 * k + 3] = rec_from_int(T(0), (unsigned)q.i1);
+              rec[5 + 5 * k + 4] = rec_from_int(T(0), (unsigned)q.i2);
+#pragma unroll
+              for (int c = 0; c < 6; ++c) rec[25 + 6 * k + c] = vert[k][c];
+            }
+          }
+          __threadfence_block();  // record + this thread's slot reads before the two flags
+        }
+        __syncwarp();
+        if (done) {
+          if (half == 0) {
+            st_vol(&ready[idx % kRingRecords], idx / kRingRecords + 1u);
+            st_vol(&ctrl[cslot], kSlotFree);
+          }
+          state = kWait;
+        }
+      };
       retire(finished);
     }
-    }  // SC == 0
     __syncwarp();
     if (lane == 0) {
       __threadfence_block();
@@ -982,7 +811,7 @@ gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, 
       if (__all_sync(0xffffffffu, exited == (1u << (kSlots / 32)) - 1u)) break;
       if (!any) __nanosleep(100);
     }
-  } else if (warp == CW + 1) {
+  } else {
     // ================================================ finisher ===============================================
     unsigned cur = 0;
     for (;;) {
@@ -1037,44 +866,6 @@ gjk_slots_ws_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, 
       __threadfence_block();
       cur += (unsigned)c;
       if (lane == 0) st_vol(&ring_ctl[1], cur);
-    }
-  } else if constexpr (SC != 0) {
-    // ================================================ scanners ===============================================
-    // thread (slot, body): waits for the owner's request, scans its body along -v (body 1) or +v (body 2), posts
-    // (maximum, lowest index attaining it).  Warps CW+2 .. 2CW+1 serve body 1 of slots 0.., the next CW warps body 2.
-    const int st = tid - (CW + 2) * 32;
-    const int sslot = st % kSlots, sbody = st / kSlots;
-    const T* body = reinterpret_cast<const T*>(slots + (size_t)sslot * sbytes + (sbody ? lay.body2 : 0u));
-    const int nvb = sbody ? nv2 : nv1;
-    const uint32_t bar = smem_addr(&bars[sslot]);
-    unsigned seen = 0;  // last request served (seq | parity << 15); 0 = none
-    bool gone = false;
-    for (;;) {
-      unsigned tag = 0;
-      u64 hi = 0;
-      if (!gone) {
-        hi = ld_vol64(&req[2 * sslot + 1]);
-        tag = (unsigned)(hi >> 32) & 0xffffu;
-        if (tag == kSeqExit) gone = true;
-      }
-      if (__all_sync(0xffffffffu, gone)) break;
-      const bool go = !gone && tag != seen && tag != 0u;
-      if (!__any_sync(0xffffffffu, go)) continue;  // spin: the request hand-over is on every iteration's critical path
-      if (go) {
-        __threadfence_block();
-        const u64 lo = ld_vol64(&req[2 * sslot]);
-        // acquire the TMA writes of this slot's current phase (the owner saw the phase complete before it published)
-        while (!mbar_test_wait(bar, tag >> 15)) {
-        }
-        V3<T> v = mk<T>(__uint_as_float((unsigned)lo), __uint_as_float((unsigned)(lo >> 32)), __uint_as_float((unsigned)hi));
-        if (!sbody) v = vneg(v);
-        T best;
-        int idx;
-        scan_slot(body, nvb, v, zero, best, idx);
-        __threadfence_block();  // slot reads before the result (the owner may free the slot once it has both)
-        st_vol64(&res[2 * sslot + sbody], (u64)__float_as_uint((float)best) | ((u64)tag << 32) | ((u64)(unsigned)idx << 48));
-        seen = tag;
-      }
     }
   }
 }

@@ -322,18 +322,7 @@ int ws_compute_warps(int nv1, int nv2, int esize) {
   int lp;
   return ws_config(nv1, nv2, &lp, esize);
 }
-// scanner warps (gjk_slots.cuh, SC = 1): fp32, one owner lane per pair, the mailboxes must fit beside the slots.
-// Development override OGJK_WS_SC=0|1.
-template <typename T>
-bool ws_use_scanners(int cw, int lp, int nv1, int nv2) {
-  if (sizeof(T) != 4 || lp != 1 || (cw != 4 && cw != 2)) return false;
-  const char* e = getenv("OGJK_WS_SC");
-  if (e && atoi(e) == 0) return false;
-  const int nslots = cw * 32;
-  return ws_fixed_bytes(nslots, 4, 1) + (size_t)nslots * slot_bytes(nv1, nv2, 4) + kSlotPadBytes <= 227u * 1024u;
-}
-
-template <typename T, int CW, int LP, int SC>
+template <typename T, int CW, int LP>
 int launch_gjk_slots_ws_cw(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist, T* nrm,
                            int* queue, int* count, const CollisionPair* pairs) {
   const uint16_t* utab = nullptr;
@@ -342,12 +331,12 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const T* c1, int nv2, const T* c2, Si
   if (int rc = ticket_buffer(&ticket)) return rc;
   constexpr int nslots = CW * 32 / LP;
   constexpr int es = (int)sizeof(T);
-  const size_t smem = (size_t)ws_fixed_bytes(nslots, es, SC) + kSlotPadBytes + (size_t)nslots * ws_slot_layout(nv1, nv2, LP, es).stride;
-  constexpr int threads = (CW + 2 + 2 * CW * SC) * 32;
-  constexpr bool eq_ok = LP == 1 && es == 4 && SC == 0;  // the interleaved two-body scan exists for fp32 only
-  auto kern = pairs ? gjk_slots_ws_kernel<T, CW, LP, eq_ok, true, SC>  // one pool: equal vertex counts by construction
-                    : (eq_ok && nv1 == nv2) ? gjk_slots_ws_kernel<T, CW, LP, eq_ok, false, SC>
-                                            : gjk_slots_ws_kernel<T, CW, LP, false, false, SC>;
+  const size_t smem = (size_t)ws_fixed_bytes(nslots, es) + kSlotPadBytes + (size_t)nslots * ws_slot_layout(nv1, nv2, LP, es).stride;
+  constexpr int threads = (CW + 2) * 32;
+  constexpr bool eq_ok = LP == 1 && es == 4;  // the interleaved two-body scan exists for fp32 only
+  auto kern = pairs ? gjk_slots_ws_kernel<T, CW, LP, eq_ok, true>  // one pool: equal vertex counts by construction
+                    : (eq_ok && nv1 == nv2) ? gjk_slots_ws_kernel<T, CW, LP, eq_ok, false>
+                                            : gjk_slots_ws_kernel<T, CW, LP, false, false>;
   long long grid = 0;
   if (int rc = persistent_grid(kern, threads, smem, &grid)) return rc;
   const long long need = ((long long)n + nslots - 1) / nslots;
@@ -362,17 +351,13 @@ int launch_gjk_slots_ws(int n, int nv1, const T* c1, int nv2, const T* c2, Simpl
                         int* queue, int* count, const CollisionPair* pairs = nullptr) {
   int lp = 1;
   const int cw = ws_config(nv1, nv2, &lp, (int)sizeof(T));
-  if (cw == 8 && lp == 1) return launch_gjk_slots_ws_cw<T, 8, 1, 0>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  if (cw == 8 && lp == 1) return launch_gjk_slots_ws_cw<T, 8, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
   if constexpr (sizeof(T) == 4) {
     if (cw == 8 && lp == 2)
-      return launch_gjk_slots_ws_cw<T, 8, 2, 0>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
-    if (ws_use_scanners<T>(cw, lp, nv1, nv2)) {
-      if (cw == 4) return launch_gjk_slots_ws_cw<T, 4, 1, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
-      return launch_gjk_slots_ws_cw<T, 2, 1, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
-    }
+      return launch_gjk_slots_ws_cw<T, 8, 2>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
   }
-  if (cw == 4) return launch_gjk_slots_ws_cw<T, 4, 1, 0>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
-  if (cw == 2) return launch_gjk_slots_ws_cw<T, 2, 1, 0>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  if (cw == 4) return launch_gjk_slots_ws_cw<T, 4, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
+  if (cw == 2) return launch_gjk_slots_ws_cw<T, 2, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
   return 1;
 }
 

@@ -5,7 +5,7 @@ mkdir -p $out
 timeout 900 python -m pytest tests/test_gpu_slots.py tests/test_gpu_epa.py tests/test_ref_vis_pinning.py -m gpu -x -q > $out/${tag}_pytest.txt 2>&1
 echo "pytest exit $?" >> $out/${tag}_pytest.txt
 tail -8 $out/${tag}_pytest.txt
-timeout 200 python tests/golden/make_vis_golden.py $out/vis_ref_float32.npz > $out/${tag}_vis_golden.txt 2>&1
+timeout 200 python tests/golden/make_vis_golden.py $out/vis_reference_kernels.npz > $out/${tag}_vis_golden.txt 2>&1
 tail -3 $out/${tag}_vis_golden.txt
 {
   for sc in 0 1; do

@@ -1,8 +1,8 @@
-"""Generates tests/golden/vis_ref_float32.npz: outputs of the REFERENCE's own visualiser kernels (broad phase, world
+"""Generates tests/golden/vis_reference_kernels.npz: outputs of the REFERENCE's own visualiser kernels (broad phase, world
 transform, contact response, descriptor upkeep -- visualization/integrate_final_gjk.cu:304-332, 467-570, 572-704,
 compiled unmodified by oracle/build_ref_vis.sh) on seeded inputs.  Needs a GPU and oracle/_ref_gpu/libogjk_refvis_f32.so:
 
-    gpurun -- 'python tests/golden/make_vis_golden.py gpurun_out/vis_ref_float32.npz'
+    gpurun -- 'python tests/golden/make_vis_golden.py gpurun_out/vis_reference_kernels.npz'
 
 The file pins the numpy restatements oracle/{broadphase,transform,contact}_oracle.py (tests/test_ref_vis_pinning.py,
 CPU) so that SURVEY.md section 8(f) rows 1-3 are checked against the reference itself, not only against restatements.
@@ -125,4 +125,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "vis_ref_float32.npz"))
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "vis_reference_kernels.npz"))

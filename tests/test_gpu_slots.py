@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def force_kernel():
-    saved = {k: os.environ.get(k) for k in ("OGJK_GJK_KERNEL", "OGJK_WS_MIN_SLOT", "OGJK_WS_LP", "OGJK_WS_SC")}
+    saved = {k: os.environ.get(k) for k in ("OGJK_GJK_KERNEL", "OGJK_WS_MIN_SLOT", "OGJK_WS_LP")}
 
     def setter(name, ws_min_slot=None):
         os.environ["OGJK_GJK_KERNEL"] = name
@@ -41,18 +41,13 @@ def _device_batch(pkg, a, b, dtype=np.float32):
     return eng, d_a, d_b, d_simp, d_dist, d_nrm
 
 
-@pytest.mark.parametrize("kernel", ["slots", "slotsws", "slotsws_noscan"])
+@pytest.mark.parametrize("kernel", ["slots", "slotsws"])
 @pytest.mark.parametrize("nv1,nv2,spread", [(64, 64, 10.0), (32, 32, 1.0), (32, 32, 10.0), (8, 8, 10.0), (4, 4, 2.0),
                                             (12, 20, 3.0), (64, 16, 6.0), (68, 68, 8.0), (16, 16, 0.5), (96, 96, 4.0), (128, 64, 5.0),
                                             (140, 140, 10.0)])
 def test_slot_kernels_match_oracle(pkg, oracle_mod, force_kernel, kernel, nv1, nv2, spread):
-    """slotsws = the warp-specialised kernel as shipped (scanner warps where 128 or 64 slots fit an SM);
-    slotsws_noscan = the same kernel with OGJK_WS_SC=0 (owner threads scan both bodies themselves)"""
     import torch
     n = 40000
-    if kernel == "slotsws_noscan":
-        os.environ["OGJK_WS_SC"] = "0"
-        kernel = "slotsws"
     a = pkg.workloads.random_polytopes(n, nv1, spread, 11, np.float32, stream=1)
     b = pkg.workloads.random_polytopes(n, nv2, spread, 11, np.float32, stream=2)
     eng, d_a, d_b, d_simp, d_dist, _ = _device_batch(pkg, a, b)

@@ -4,7 +4,7 @@ The numpy restatements (oracle/broadphase_oracle.py, transform_oracle.py, contac
 against brute force / their own loops.  Here they -- and on the GPU box the product's kernels -- are compared with
 outputs of the reference visualiser's own kernels (visualization/integrate_final_gjk.cu:304-332, 467-570, 572-704,
 compiled unmodified by oracle/build_ref_vis.sh):
-  * CPU tests read tests/golden/vis_ref_float32.npz, generated on a B200 by tests/golden/make_vis_golden.py;
+  * CPU tests read tests/golden/vis_reference_kernels.npz, generated on a B200 by tests/golden/make_vis_golden.py;
   * GPU tests run the reference kernels live (oracle/_ref_gpu/libogjk_refvis_f32.so travels to the box).
 What "equal" means per kernel: broad phase -- the same pair SET (the reference's order inside an object's group
 follows atomic slot order) except pairs whose spheres touch within rounding, because the reference's visualiser is
@@ -21,7 +21,7 @@ import pytest
 
 from conftest import ROOT
 
-GOLDEN = os.path.join(ROOT, "tests", "golden", "vis_ref_float32.npz")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "vis_reference_kernels.npz")
 
 
 def _load(name):
@@ -33,7 +33,7 @@ def _load(name):
 
 def _golden():
     if not os.path.exists(GOLDEN):
-        pytest.skip("tests/golden/vis_ref_float32.npz not generated yet (needs a GPU: tests/golden/make_vis_golden.py)")
+        pytest.skip("tests/golden/vis_reference_kernels.npz not generated yet (needs a GPU: tests/golden/make_vis_golden.py)")
     return np.load(GOLDEN)
 
 
