@@ -70,6 +70,9 @@ int ogjk_memcpy_to_device(void* d_dst, const void* src, size_t bytes);
 int ogjk_memcpy_from_device(void* dst, const void* d_src, size_t bytes);
 /* Number of kernels this library has launched on the calling thread since the last reset (bench accounting). */
 long long ogjk_launch_count(int reset);
+/* Name of the kernel family the calling thread launched last ("gjk slots (fp16 pre-scan) kernel", "epa kernel", ...):
+ * lets a test or a benchmark state which kernel produced a result. */
+const char* ogjk_last_kernel(void);
 /* Uniform-grid broad phase on the device (the step before the hot path in the reference's caller:
  * visualization/integrate_final_gjk.cu:467-570 insert/count/generate kernels, :916-1002 sim_broad_phase).
  * d_pos_radius: num_objects x float4 = centre xyz + bounding radius.  An object lives in the cell

@@ -67,6 +67,7 @@ def load_library() -> ctypes.CDLL:
         lib.ogjk_last_error.restype = ctypes.c_char_p
         lib.ogjk_version.restype = ctypes.c_char_p
         lib.ogjk_launch_count.restype = ctypes.c_longlong
+        lib.ogjk_last_kernel.restype = ctypes.c_char_p
         _lib = lib
     return _lib
 
@@ -191,6 +192,9 @@ class Engine:
 
     def release_pool(self, d_polytopes):
         self.lib.ogjk_release_pool(_ptr(d_polytopes))
+
+    def last_kernel(self) -> str:
+        return self.lib.ogjk_last_kernel().decode()
 
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.ogjk_launch_count(ctypes.c_int(int(reset))))

@@ -27,6 +27,7 @@
 #include "gjk_generic.cuh"
 #include "gjk_tables.h"
 #include "gjk_slots.cuh"
+#include "gjk_slots16.cuh"
 #include "gjk_uniform.cuh"
 #include "ogjk_types.h"
 
@@ -38,6 +39,7 @@ thread_local std::string t_err;
 thread_local cudaStream_t t_stream = nullptr;
 thread_local bool t_sync = true;
 thread_local long long t_launches = 0;
+thread_local const char* t_last_kernel = "";  // name of the last kernel launched through finish_launch
 
 // optional per-stage device timing of the fused GJK+EPA entry points (ogjk_set_timing / ogjk_stage_times): three
 // events per call on the launching stream -- before GJK, between the stages, after EPA
@@ -116,6 +118,7 @@ int device_unified_table(const uint16_t** out) {
 
 int finish_launch(const char* what) {
   ++t_launches;
+  t_last_kernel = what;
   OGJK_CK(cudaGetLastError());
   if (t_sync) {
     cudaError_t e = cudaStreamSynchronize(t_stream);
@@ -270,7 +273,7 @@ int ticket_buffer(unsigned** out) {
 int forced_kernel() {
   const char* e = getenv("OGJK_GJK_KERNEL");
   return !e ? 0 : !strcmp(e, "slots") ? 1 : !strcmp(e, "uniform") ? 2 : !strcmp(e, "generic") ? 3 :
-         !strcmp(e, "slotsws") ? 4 : 0;
+         !strcmp(e, "slotsws") ? 4 : !strcmp(e, "slots16") ? 5 : !strcmp(e, "slotsws32") ? 6 : 0;
 }
 
 template <typename T>
@@ -346,9 +349,69 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const T* c1, int nv2, const T* c2, Si
                                                     nrm, queue, count, pairs, ws_dense_chunk());
   return finish_launch("gjk slots (warp-specialised) kernel");
 }
+// ---- fp16 pre-scan slot kernel (gjk_slots16.cuh): fp32 batches whose bodies have 8 * NB vertices, NB in 4..8 ---------
+// Takes over from the warp-specialised fp32-slot kernel wherever that one is down to 128 slots per SM (one compute warp
+// per scheduler).  OGJK_GJK_KERNEL=slots16 forces it for every supported shape, =slotsws32 keeps the fp32 slots;
+// OGJK_S16_CFG=<NC><P> (development) picks another converter configuration for the 64+64-vertex dense instance.
+bool slots16_shape(int nv1, int nv2) { return nv1 == nv2 && nv1 % 8 == 0 && nv1 >= 32 && nv1 <= 64; }
+bool use_slots16(int nv1, int nv2, int esize) {
+  if (esize != 4 || !slots16_shape(nv1, nv2)) return false;
+  const int force = forced_kernel();
+  if (force == 5) return true;
+  if (force != 0) return false;
+  int lp = 1;
+  return ws_config(nv1, nv2, &lp, esize) == 4;  // 128 fp32 slots: 40..64 vertices per body
+}
+template <int NB, bool IDX, int NC, int P>
+int launch_gjk_slots16_inst(int n, const float* c1, const float* c2, SimplexT<float>* simp, float* dist, float* nrm,
+                            int* queue, int* count, const CollisionPair* pairs) {
+  const uint16_t* utab = nullptr;
+  if (int rc = device_unified_table(&utab)) return rc;
+  unsigned* ticket = nullptr;
+  if (int rc = ticket_buffer(&ticket)) return rc;
+  constexpr size_t smem = s16_smem_bytes(NB, NB);
+  static_assert(smem <= 227u * 1024u, "slots do not fit");
+  constexpr int threads = (kS16ComputeWarps + NC + 1) * 32;
+  auto kern = gjk_slots16_kernel<NB, NB, IDX, NC, P>;
+  long long grid = 0;
+  if (int rc = persistent_grid(kern, threads, smem, &grid)) return rc;
+  const long long need = ((long long)n + kS16Slots - 1) / kS16Slots;
+  if (grid > need) grid = need;
+  OGJK_CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned), t_stream));
+  kern<<<(unsigned)grid, threads, smem, t_stream>>>(c1, c2, simp, dist, (unsigned)n, utab, ticket, nrm, queue, count, pairs);
+  return finish_launch("gjk slots (fp16 pre-scan) kernel");
+}
+template <int NB>
+int launch_gjk_slots16_nb(int n, const float* c1, const float* c2, SimplexT<float>* simp, float* dist, float* nrm,
+                          int* queue, int* count, const CollisionPair* pairs) {
+  if (pairs) return launch_gjk_slots16_inst<NB, true, 4, 6>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+  if constexpr (NB == 8) {
+    const char* e = getenv("OGJK_S16_CFG");
+    const int cfg = e ? atoi(e) : 0;
+    if (cfg == 44) return launch_gjk_slots16_inst<NB, false, 4, 4>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+    if (cfg == 48) return launch_gjk_slots16_inst<NB, false, 4, 8>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+    if (cfg == 83) return launch_gjk_slots16_inst<NB, false, 8, 3>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+    if (cfg == 84) return launch_gjk_slots16_inst<NB, false, 8, 4>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+  }
+  return launch_gjk_slots16_inst<NB, false, 4, 6>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+}
+int launch_gjk_slots16(int n, int nv, const float* c1, const float* c2, SimplexT<float>* simp, float* dist, float* nrm,
+                       int* queue, int* count, const CollisionPair* pairs) {
+  switch (nv / 8) {
+    case 4: return launch_gjk_slots16_nb<4>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+    case 5: return launch_gjk_slots16_nb<5>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+    case 6: return launch_gjk_slots16_nb<6>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+    case 7: return launch_gjk_slots16_nb<7>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+    default: return launch_gjk_slots16_nb<8>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+  }
+}
+
 template <typename T>
 int launch_gjk_slots_ws(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist, T* nrm,
                         int* queue, int* count, const CollisionPair* pairs = nullptr) {
+  if constexpr (sizeof(T) == 4) {
+    if (use_slots16(nv1, nv2, 4)) return launch_gjk_slots16(n, nv1, c1, c2, simp, dist, nrm, queue, count, pairs);
+  }
   int lp = 1;
   const int cw = ws_config(nv1, nv2, &lp, (int)sizeof(T));
   if (cw == 8 && lp == 1) return launch_gjk_slots_ws_cw<T, 8, 1>(n, nv1, c1, nv2, c2, simp, dist, nrm, queue, count, pairs);
@@ -381,7 +444,7 @@ int launch_gjk_slots_if(int n, int nv1, const T* c1, int nv2, const T* c2, Simpl
   constexpr int es = (int)sizeof(T);
   const int force = forced_kernel();
   if (force == 2 || force == 3) return 1;
-  if (force == 4 || (force == 0 && n >= 32768 && use_ws_kernel(nv1, nv2, es)))
+  if (force >= 4 || (force == 0 && n >= 32768 && use_ws_kernel(nv1, nv2, es)))
     return launch_gjk_slots_ws<T>(n, nv1, c1, nv2, c2, simp, dist, nullptr, nullptr, nullptr);
   if ((size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2, es) > 227u * 1024u) return 1;
   if (force == 0 && n < 32768) return 1;
@@ -540,7 +603,7 @@ int launch_gjk_epa_uniform(int n, int nv1, const T* c1, int nv2, const T* c2, Si
   {
     const bool aligned = (((uintptr_t)c1 | (uintptr_t)c2) & 15u) == 0 && nv1 % 4 == 0 && nv2 % 4 == 0;
     const int force = forced_kernel();
-    if (aligned && n >= 32768 && (force == 0 || force == 4) && use_ws_kernel(nv1, nv2, (int)sizeof(T))) {
+    if (aligned && n >= 32768 && (force == 0 || force >= 4) && use_ws_kernel(nv1, nv2, (int)sizeof(T))) {
       EpaQueue q;
       if (int rc = epa_queue_buffers((size_t)n, &q)) return rc;
       const bool sync_saved = t_sync;
@@ -640,7 +703,7 @@ int launch_indexed_uniform(int n, const PoolInfo& pool, const CollisionPair* d_p
   const T* base = (const T*)pool.coords;
   const int force = forced_kernel();
   if (nv <= 0 || nv % 4 || n < 32768 || force == 2 || force == 3 || !(stages & kGjkStage)) return 1;
-  const bool ws = force == 4 || (force == 0 && use_ws_kernel(nv, nv, es));
+  const bool ws = force >= 4 || (force == 0 && use_ws_kernel(nv, nv, es));
   const bool v2_fits = (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv, nv, es) <= 227u * 1024u;
   if (!ws && !v2_fits) return 1;
   if (ws && ws_compute_warps(nv, nv, es) == 0) return 1;
@@ -1486,6 +1549,7 @@ int ogjk_memcpy_from_device(void* dst, const void* d_src, size_t bytes) {
   OGJK_CK(cudaStreamSynchronize(t_stream));
   return 0;
 }
+const char* ogjk_last_kernel(void) { return t_last_kernel; }
 long long ogjk_launch_count(int reset) {
   const long long v = t_launches;
   if (reset) t_launches = 0;

@@ -94,12 +94,14 @@ def _oracle(oracle_mod, dtype):
     return oracle_mod.Oracle(kind, dtype)
 
 
-@pytest.mark.parametrize("kernel", ["slotsws", "slots", "uniform", "generic"])
+@pytest.mark.parametrize("kernel", ["slots16", "slotsws32", "slots", "uniform", "generic"])
 @pytest.mark.parametrize("nv", [64, 32, 8])
 def test_gjk_degenerate_fp32(pkg, oracle_mod, force_kernel, kernel, nv):
     import torch
     if kernel == "uniform" and nv <= 16:
         pytest.skip("the register-resident kernel is not used below 17 vertices")
+    if kernel == "slots16" and nv < 32:
+        pytest.skip("the fp16 pre-scan kernel takes 32..64 vertices per body")
     n = 40000
     a, b, cat = degenerate_pairs(n, nv, seed=5 + nv)
     eng = pkg.Engine(np.float32)
