@@ -18,12 +18,15 @@
 // with it every later bit of the iteration -- is the reference's.  On the benchmark generator 1.19 vertices per scan
 // are candidates (83 % of the scans: one).
 //
-// Roles (one CTA per SM, 8 + NC + 1 warps):
+// Roles (one CTA per SM, 8 + 8 + 1 warps):
 //   * compute warps: ONE THREAD PER PAIR as in gjk_slots.cuh (rotated loop, lane-uniform iteration gjk_substep_u);
-//   * converter warps replace the TMA loader: they poll the slot flags, draw tickets, fetch the pair's two fp32 vertex
-//     sets with 128-bit loads (lane l: four consecutive vertices), centre / scale / convert them and write the fp16
-//     slot in blocks of eight vertices  x0..x7 | y0..y7 | z0..z7  (three 128-bit shared loads per block in the scan);
-//     the bytes in flight that the TMA version kept in idle slots are held in the converters' registers;
+//   * converter warps replace the TMA loader, one per compute warp: each polls the 32 slot flags of its compute warp,
+//     draws tickets, fetches a pair's two fp32 vertex sets with 128-bit loads (lane l: four consecutive vertices),
+//     centres / scales / converts them (packed FADD2 / FMUL2) and writes the fp16 slot in blocks of eight vertices
+//     x0..x7 | y0..y7 | z0..z7  (three 128-bit shared loads per block in the scan).  The loads of D pairs rotate
+//     through a register ring, so D - 1 pairs per converter warp are in flight while one is converted: the bytes in
+//     flight that the TMA version kept in idle slots are held in the converters' registers.  A converted slot is
+//     published with an mbarrier arrive (release) -- no memory fence, which would wait for the loads in flight;
 //   * the finisher warp takes 9-word records (pair, simplex size, v, vertex indices), re-reads the <= 8 source vertices
 //     from global memory/L2, rebuilds the simplex points (the same fp32 subtraction), and runs the witness stage, the
 //     result stores and the fused EPA gate exactly as in gjk_slots.cuh.
@@ -35,12 +38,11 @@
 namespace ogjk {
 
 constexpr int kS16Slots = 256;
-constexpr int kS16ComputeWarps = 8;
+constexpr int kS16ComputeWarps = 4;   // 128 threads, TWO slots each: one being worked on, one being refilled
 constexpr int kS16RingRecords = 64;
 constexpr int kS16RecWords = 9;       // pair | n | v.xyz | polytope index 1 | polytope index 2 | vertex indices (2 words)
-constexpr int kS16ScratchWords = 25;  // finisher: 24 vertex coordinates per lane, odd stride
-enum : unsigned { kS16Free = 0u, kS16Ready = 1u, kS16Exit = 2u };
-constexpr uint32_t kS16PickBytes = 1024;  // converter batch lists: NC * P entries of 16 bytes
+constexpr int kS16Finishers = 2;      // finisher f serves compute warps 2 f and 2 f + 1 through its own record ring
+enum : unsigned { kS16Free = 0u, kS16Busy = 1u, kS16Exit = 2u };
 constexpr float kS16Scale = 16000.0f;
 constexpr float kS16WConst = 86.1f;
 constexpr float kS16WCentre = 3.7e-7f;
@@ -53,10 +55,9 @@ __host__ __device__ constexpr uint32_t s16_slot_bytes(int nb1, int nb2) {
   return units * 16u;
 }
 __host__ __device__ constexpr uint32_t s16_fixed_bytes() {
-  // table | ctrl | pair_of | idx1_of | idx2_of | ring control (16 B) | ready flags | ring | finisher scratch | batch lists
-  return kSlotTableBytes + (uint32_t)kS16Slots * 16u + 16u + (uint32_t)kS16RingRecords * 4u +
-         (((uint32_t)kS16RingRecords * kS16RecWords * 4u + 15u) & ~15u) + ((32u * kS16ScratchWords * 4u + 15u) & ~15u) +
-         kS16PickBytes;
+  // mbarriers | table | ctrl | pair_of | idx1_of | idx2_of | per finisher: ring control (16 B), ready flags, ring
+  return (uint32_t)kS16Slots * 8u + kSlotTableBytes + (uint32_t)kS16Slots * 16u +
+         (uint32_t)kS16Finishers * (16u + (uint32_t)kS16RingRecords * 4u + (((uint32_t)kS16RingRecords * kS16RecWords * 4u + 15u) & ~15u));
 }
 __host__ __device__ constexpr uint32_t s16_smem_bytes(int nb1, int nb2) {
   return s16_fixed_bytes() + (uint32_t)kS16Slots * s16_slot_bytes(nb1, nb2);
@@ -151,26 +152,65 @@ OGJK_D int next_candidate16(Cand16& c, const uint4* __restrict__ blk, __half2 dx
   return 8 * c.blk + k;
 }
 
+// the finisher's vertex fetch: the four vertex pairs of a record live in registers; the tag in bits 30..31 of the
+// index picks one with selects
+struct RegFetch16 {
+  float v[4][6];
+  OGJK_D V3<float> operator()(int body, int i) const {
+    const unsigned k = (unsigned)i >> 30;
+    const int o = 3 * body;
+    const float x = k == 0u ? v[0][o] : k == 1u ? v[1][o] : k == 2u ? v[2][o] : v[3][o];
+    const float y = k == 0u ? v[0][o + 1] : k == 1u ? v[1][o + 1] : k == 2u ? v[2][o + 1] : v[3][o + 1];
+    const float z = k == 0u ? v[0][o + 2] : k == 1u ? v[1][o + 2] : k == 2u ? v[2][o + 2] : v[3][o + 2];
+    return mk<float>(x, y, z);
+  }
+};
 OGJK_D uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+OGJK_D u64 sub2(u64 a, u64 b) {  // two individually rounded fp32 subtractions in one issue slot (FADD2)
+  u64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+OGJK_D u64 mul2s(u64 a, float s) {  // both halves times s (FMUL2)
+  u64 ss, r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(ss));
+  return r;
+}
+OGJK_D unsigned atom_add_global(unsigned* p, unsigned v) {  // one ATOMG, without the compiler's warp-aggregation prologue
+  unsigned r;
+  asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+  return r;
+}
+OGJK_D float lo32(u64 a) { return __uint_as_float((unsigned)a); }
+OGJK_D float hi32(u64 a) { return __uint_as_float((unsigned)(a >> 32)); }
+OGJK_D void mbar_arrive(uint32_t bar) {  // release at CTA scope: the slot's stores are visible to the waiting thread
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
 // NB1 / NB2: blocks of eight vertices per body (vertex counts 8 NB1 and 8 NB2, 2 (NB1 + NB2) <= 32 converter lanes).
-// IDX: pairs are gkCollisionPair records into one pool.  NC converter warps (a divisor of 8), P pairs per converter batch.
-template <int NB1, int NB2, bool IDX, int NC, int P>
-__global__ void __launch_bounds__((kS16ComputeWarps + NC + 1) * 32)
+// IDX: pairs are gkCollisionPair records into one pool.  D: depth of the converters' register ring (pairs per warp).
+constexpr int kS16Converters = kS16Slots / 32;  // converter c serves slots 32 c .. 32 c + 31
+constexpr int kS16Threads = (kS16ComputeWarps + kS16Converters + kS16Finishers) * 32;
+template <int NB1, int NB2, bool IDX, int D>
+__global__ void __launch_bounds__(kS16Threads)
 gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ coord2, SimplexT<float>* __restrict__ simplices,
                    float* __restrict__ distances, unsigned n, const uint16_t* __restrict__ utab_g,
                    unsigned* __restrict__ ticket, float* __restrict__ normals, int* __restrict__ epa_queue,
-                   int* __restrict__ epa_count, const CollisionPair* __restrict__ pairs) {
+                   int* __restrict__ epa_count, const CollisionPair* __restrict__ pairs, unsigned idle_ns, unsigned age_cycles) {
   typedef float T;
   constexpr int CW = kS16ComputeWarps;
-  constexpr int kThreads = (CW + NC + 1) * 32;
+  constexpr int NC = kS16Converters;
+  constexpr int kThreads = kS16Threads;
   constexpr int NV1 = 8 * NB1, NV2 = 8 * NB2;
   constexpr int G1 = 2 * NB1, G2 = 2 * NB2;  // converter lanes per body (four vertices each)
   static_assert(G1 + G2 <= 32, "a pair must fit the 32 lanes of a converter warp");
-  static_assert(kS16Slots % (32 * NC) == 0, "every converter lane polls a whole number of slots");
   constexpr uint32_t sbytes = s16_slot_bytes(NB1, NB2);
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* sp = smem_raw;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp);  // one mbarrier per slot: completed by the converter's arrive
+  sp += kS16Slots * 8;
   uint16_t* utab = reinterpret_cast<uint16_t*>(sp);
   sp += kSlotTableBytes;
   unsigned* ctrl = reinterpret_cast<unsigned*>(sp);
@@ -181,36 +221,44 @@ gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ c
   sp += kS16Slots * 4;
   int* idx2_of = reinterpret_cast<int*>(sp);
   sp += kS16Slots * 4;
-  unsigned* ring_ctl = reinterpret_cast<unsigned*>(sp);  // [0] tail (reserved), [1] head (consumed), [2] exited warps
-  sp += 16;
-  unsigned* ready = reinterpret_cast<unsigned*>(sp);
-  sp += kS16RingRecords * 4;
-  unsigned* ring = reinterpret_cast<unsigned*>(sp);
-  sp += (kS16RingRecords * kS16RecWords * 4 + 15) & ~15;
-  float* scratch = reinterpret_cast<float*>(sp);
-  sp += (32 * kS16ScratchWords * 4 + 15) & ~15;
-  uint4* picks = reinterpret_cast<uint4*>(sp);
-  static_assert(NC * P * 16 <= (int)kS16PickBytes, "batch lists do not fit");
+  // record rings: compute warps 0 and 1 feed finisher 0, warps 2 and 3 finisher 1
+  constexpr uint32_t kRingBytes = 16u + kS16RingRecords * 4u + ((kS16RingRecords * kS16RecWords * 4u + 15u) & ~15u);
+  const int fin_id = warp < CW ? warp / (CW / kS16Finishers) : (warp >= CW + NC ? warp - CW - NC : 0);
+  unsigned* ring_ctl = reinterpret_cast<unsigned*>(sp + fin_id * kRingBytes);  // [0] tail (reserved), [1] head (consumed), [2] exited warps
+  unsigned* ready = ring_ctl + 4;
+  unsigned* ring = ready + kS16RingRecords;
   unsigned char* slots = smem_raw + s16_fixed_bytes();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (int i = tid; i < kUnifiedSize / 2; i += kThreads)
     reinterpret_cast<uint32_t*>(utab)[i] = __ldg(reinterpret_cast<const uint32_t*>(utab_g) + i);
   for (int i = tid; i < kS16Slots; i += kThreads) {
+    mbar_init(smem_addr(&bars[i]), 1);
     ctrl[i] = kS16Free;
     pair_of[i] = 0;
   }
-  for (int i = tid; i < kS16RingRecords; i += kThreads) ready[i] = 0;
-  if (tid < 4) ring_ctl[tid] = 0;
+  for (int i = tid; i < (int)(kS16Finishers * kRingBytes / 4u); i += kThreads) reinterpret_cast<unsigned*>(sp)[i] = 0;
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
   if (warp < CW) {
     // ================================================ compute ================================================
-    const int cslot = tid;
-    const unsigned char* sbase = slots + (size_t)cslot * sbytes;
-    const float* hdr = reinterpret_cast<const float*>(sbase);
-    const uint4* blk1 = reinterpret_cast<const uint4*>(sbase + kS16HeaderBytes);
+    // slot b of this thread is slot b * 128 + tid: while the pair in one is iterated, the converters refill the other,
+    // so a finished pair is followed by the next one without waiting for memory
+    int cur = 0;            // the buffer in use (or waited for)
+    uint32_t parities = 0;  // bit b: phase parity of buffer b's mbarrier
+    unsigned gone = 0;      // bit b: buffer b has been told to exit
+    int cslot = tid;
+    const float* hdr = reinterpret_cast<const float*>(slots + (size_t)cslot * sbytes);
+    const uint4* blk1 = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(hdr) + kS16HeaderBytes);
     const uint4* blk2 = blk1 + 3 * NB1;
+    auto other_buffer = [&]() {  // switch to the other buffer unless it has been told to exit
+      if ((gone >> (cur ^ 1)) & 1u) return;
+      cur ^= 1;
+      cslot = cur * (CW * 32) + tid;
+      hdr = reinterpret_cast<const float*>(slots + (size_t)cslot * sbytes);
+      blk1 = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(hdr) + kS16HeaderBytes);
+      blk2 = blk1 + 3 * NB1;
+    };
     enum { kWait = 0, kRun = 1, kExit = 2 };
     int state = kWait;
     unsigned pair = 0;
@@ -224,9 +272,8 @@ gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ c
       if (state == kRun && need_sub) fin_sub = gjk_substep_u(g, utab);
       need_sub = false;
       if (state == kWait) {
-        const unsigned c = ld_vol(&ctrl[cslot]);
-        if (c == kS16Ready) {
-          __threadfence_block();  // acquire: the converter's slot, header and pair_of stores
+        if (mbar_test_wait(smem_addr(&bars[cslot]), (parities >> cur) & 1u)) {  // acquire: the converter's stores
+          parities ^= 1u << cur;
           pair = ld_vol(&pair_of[cslot]);
           pi1 = pi2 = (int)pair;
           if (IDX) {
@@ -237,9 +284,11 @@ gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ c
           g2 = coord2 + (size_t)pi2 * (NV2 * 3);
           gjk_init(g, mk<T>(hdr[0], hdr[1], hdr[2]), mk<T>(hdr[6], hdr[7], hdr[8]));
           state = kRun;
-        } else if (c == kS16Exit) {
-          state = kExit;
+        } else if (ld_vol(&ctrl[cslot]) == kS16Exit) {  // no more work for this buffer: leave when both have been told
+          gone |= 1u << cur;
+          if (gone == 3u) state = kExit;
         }
+        if (state == kWait) other_buffer();  // not ready: look at the other buffer next trip
       }
       if (__all_sync(0xffffffffu, state == kExit)) break;
       if (!__any_sync(0xffffffffu, state == kRun)) __nanosleep(32);  // start-up / drain
@@ -318,6 +367,7 @@ gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ c
             st_vol(&ready[idx % kS16RingRecords], idx / kS16RingRecords + 1u);
             st_vol(&ctrl[cslot], kS16Free);
             state = kWait;
+            other_buffer();  // refilled while this pair was iterated
           }
         }
       }
@@ -329,169 +379,166 @@ gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ c
     }
   } else if (warp < CW + NC) {
     // =============================================== converter ===============================================
-    constexpr int kPer = kS16Slots / NC;  // slots served by this warp
-    constexpr int kWords = kPer / 32;
-    const int first = (warp - CW) * kPer;
-    const bool second = lane >= G1;  // this lane converts four vertices of body 2
+    const int first = (warp - CW) * 32;  // this warp serves the 32 slots of compute warp (warp - CW)
+    const bool second = lane >= G1;      // this lane converts four vertices of body 2
     const bool act = lane < G1 + G2;
     const int lg = second ? lane - G1 : lane;  // 4-vertex group within the body
     const int src0 = second ? G1 : 0;          // lane holding the body's first vertex
     const uint32_t lane_off = kS16HeaderBytes + (uint32_t)(second ? NB1 * 48 : 0) + (uint32_t)(lg >> 1) * 48u + (uint32_t)(lg & 1) * 8u;
-    uint4* pk = picks + (warp - CW) * P;  // this warp's batch: (slot, ticket, polytope index 1, polytope index 2)
-    const unsigned lt = (1u << lane) - 1u;
-    unsigned tk_next = 0, tk_end = 0;  // reserved ticket range (warp-uniform)
-    unsigned raw = 0;                  // lane 0: result of the atomic that reserves the NEXT range, issued ahead of need
+    const float* const lane_src = (second ? coord2 : coord1) + lg * 12;
+    constexpr int kBodyFloats1 = NV1 * 3, kBodyFloats2 = NV2 * 3;
+    // tickets (warp-uniform state): the range in use [tk_next, tk_end) and a spare one [sp_next, sp_end) that is
+    // requested (one atomic by lane 0) and collected at the top of the ring loop, a whole pass apart, so that neither
+    // the atomic's round trip nor -- for indexed batches -- the load of the range's pair records is ever waited for
+    unsigned tk_next = 0, tk_end = 0, tk_base = 0, sp_next = 0, sp_end = 0;
+    unsigned raw = 0;  // lane 0: result of the atomic in flight
     bool pending = false;
+    int rec1 = 0, rec2 = 0, srec1 = 0, srec2 = 0;  // IDX: this lane's pair record of the range in use / the spare range
+    unsigned busy = 0;       // slots picked but not yet published
     int exited = 0;
+    // the register ring: up to D pairs whose loads are in flight.  An entry is converted once it is `age_cycles` old
+    // (about the latency of its loads): converting it earlier would block the warp on the scoreboard and with it the
+    // loads of the slots that fall free in the meantime
+    uint4 q[D][3];
+    unsigned stamp[D];
+    int sl[D];
+    unsigned tk[D];
+    int ri1[D], ri2[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) sl[k] = -1;
     for (;;) {
-      // ---- collect up to P free slots of this warp's range: lane l watches slots first + l (+ 32, ...) ----
-      unsigned fm[kWords];
-      unsigned total = 0;
-#pragma unroll
-      for (int j = 0; j < kWords; ++j) {
-        fm[j] = __ballot_sync(0xffffffffu, ld_vol(&ctrl[first + 32 * j + lane]) == kS16Free);
-        total += __popc(fm[j]);
-      }
-      if (total == 0) {
-        if (exited == kPer) break;
-        __nanosleep(40);
-        continue;
-      }
-      __threadfence_block();  // acquire: the owners' last slot reads precede the flags
-      const unsigned cnt = total < (unsigned)P ? total : (unsigned)P;
-      // tickets: ranks below `avail` come from the range in hand, the others from the next one
-      const unsigned avail = tk_end - tk_next;
-      unsigned nb = 0;
-      if (cnt > avail) {
-        if (!pending && lane == 0) raw = atomicAdd(ticket, kTicketChunk);
-        nb = __shfl_sync(0xffffffffu, raw, 0);
-        pending = false;
-      }
-      {
-        unsigned before = 0;
-#pragma unroll
-        for (int j = 0; j < kWords; ++j) {
-          const unsigned r = before + __popc(fm[j] & lt);
-          if (((fm[j] >> lane) & 1u) && r < cnt) {
-            const unsigned t = r < avail ? tk_next + r : nb + (r - avail);
-            int a = (int)t, b = (int)t;
-            if (IDX && t < n) {
-              const CollisionPair pr = pairs[t];
-              a = pr.idx1;
-              b = pr.idx2;
-            }
-            pk[r] = make_uint4((unsigned)(32 * j + lane), t, (unsigned)a, (unsigned)b);
-          }
-          before += __popc(fm[j]);
-        }
-      }
-      if (cnt > avail) {
-        tk_next = nb + (cnt - avail);
-        tk_end = nb + kTicketChunk;
-      } else {
-        tk_next += cnt;
-      }
-      __syncwarp();
-      int sl[P];
-      unsigned tk[P];
-      int i1[P], i2[P];
-      uint4 q[P][3];
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        const uint4 e = pk[k < (int)cnt ? k : 0];
-        sl[k] = (int)e.x;
-        tk[k] = e.y;
-        i1[k] = (int)e.z;
-        i2[k] = (int)e.w;
-      }
-      __syncwarp();  // the list is read before the next batch overwrites it
-      // ---- all loads of the batch first: these registers are the bytes in flight ----
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        if (k < (int)cnt && tk[k] < n && act) {
-          const float* src = (second ? coord2 + (size_t)i2[k] * (NV2 * 3) : coord1 + (size_t)i1[k] * (NV1 * 3)) + lg * 12;
-          q[k][0] = ldg128(src);
-          q[k][1] = ldg128(src + 4);
-          q[k][2] = ldg128(src + 8);
+      if (sp_next == sp_end) {
+        if (!pending) {
+          if (lane == 0) raw = atom_add_global(ticket, kTicketChunk);
+          pending = true;
         } else {
-          q[k][0] = q[k][1] = q[k][2] = make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
-      if (!pending && tk_end - tk_next < (unsigned)P) {  // reserve the next ticket range behind the loads
-        if (lane == 0) raw = atomicAdd(ticket, kTicketChunk);
-        pending = true;
-      }
-      // ---- centre, scale, convert, store, publish ----
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        if (k >= (int)cnt) break;
-        const int s = first + sl[k];
-        if (tk[k] >= n) {  // out of work: the slot's owner may leave
-          if (lane == 0) st_vol(&ctrl[s], kS16Exit);
-          ++exited;
-          continue;
-        }
-        float f[12];
-        f[0] = __uint_as_float(q[k][0].x); f[1] = __uint_as_float(q[k][0].y); f[2] = __uint_as_float(q[k][0].z);
-        f[3] = __uint_as_float(q[k][0].w); f[4] = __uint_as_float(q[k][1].x); f[5] = __uint_as_float(q[k][1].y);
-        f[6] = __uint_as_float(q[k][1].z); f[7] = __uint_as_float(q[k][1].w); f[8] = __uint_as_float(q[k][2].x);
-        f[9] = __uint_as_float(q[k][2].y); f[10] = __uint_as_float(q[k][2].z); f[11] = __uint_as_float(q[k][2].w);
-        const float cx = __shfl_sync(0xffffffffu, f[0], src0), cy = __shfl_sync(0xffffffffu, f[1], src0),
-                    cz = __shfl_sync(0xffffffffu, f[2], src0);
-        float e[12];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          e[3 * i] = sub_rn(f[3 * i], cx);
-          e[3 * i + 1] = sub_rn(f[3 * i + 1], cy);
-          e[3 * i + 2] = sub_rn(f[3 * i + 2], cz);
-        }
-        float m = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) m = fmaxf(m, fabsf(e[i]));
-        const unsigned mb = act ? __float_as_uint(m) : 0u;  // non-negative floats order like their bit patterns
-        const unsigned r1 = __reduce_max_sync(0xffffffffu, second ? 0u : mb);
-        const unsigned r2 = __reduce_max_sync(0xffffffffu, second ? mb : 0u);
-        const float mm = __uint_as_float(second ? r2 : r1);
-        const bool ok = mm > 8.67361737988e-19f;  // 2^-60
-        const float sc = ok ? __fdividef(kS16Scale, mm) : 0.0f;
-        unsigned h[6];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const __half2 lo = __floats2half2_rn(mul_rn(e[c], sc), mul_rn(e[3 + c], sc));
-          const __half2 hi = __floats2half2_rn(mul_rn(e[6 + c], sc), mul_rn(e[9 + c], sc));
-          h[2 * c] = *reinterpret_cast<const unsigned*>(&lo);
-          h[2 * c + 1] = *reinterpret_cast<const unsigned*>(&hi);
-        }
-        unsigned char* dst = slots + (size_t)s * sbytes;
-        if (act) {
-          *reinterpret_cast<uint2*>(dst + lane_off) = make_uint2(h[0], h[1]);
-          *reinterpret_cast<uint2*>(dst + lane_off + 16) = make_uint2(h[2], h[3]);
-          *reinterpret_cast<uint2*>(dst + lane_off + 32) = make_uint2(h[4], h[5]);
-          if (lg == 0) {
-            float* hd = reinterpret_cast<float*>(dst) + (second ? 6 : 0);
-            hd[0] = f[0];
-            hd[1] = f[1];
-            hd[2] = f[2];
-            hd[3] = ok ? fmaf(kS16WCentre * sc, fabsf(f[0]), kS16WConst) : 1e30f;
-            hd[4] = ok ? fmaf(kS16WCentre * sc, fabsf(f[1]), kS16WConst) : 1e30f;
-            hd[5] = ok ? fmaf(kS16WCentre * sc, fabsf(f[2]), kS16WConst) : 1e30f;
-          }
-        }
-        if (lane == 0) {
-          pair_of[s] = tk[k];
+          sp_next = __shfl_sync(0xffffffffu, raw, 0);
+          sp_end = sp_next + kTicketChunk;
+          pending = false;
           if (IDX) {
-            idx1_of[s] = i1[k];
-            idx2_of[s] = i2[k];
+            srec1 = srec2 = 0;
+            if (sp_next + lane < n) {
+              const CollisionPair pr = pairs[sp_next + lane];
+              srec1 = pr.idx1;
+              srec2 = pr.idx2;
+            }
           }
         }
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) st_vol(&ctrl[s], kS16Ready);
       }
+      if (tk_next == tk_end && sp_next != sp_end) {  // the range in use is exhausted: the spare takes over
+        tk_base = tk_next = sp_next;
+        tk_end = sp_end;
+        sp_next = sp_end;
+        rec1 = srec1;
+        rec2 = srec2;
+      }
+      // free slots of this warp's range, looked at once per pass
+      unsigned fm = __ballot_sync(0xffffffffu, ld_vol(&ctrl[first + lane]) == kS16Free) & ~busy;
+      const unsigned now = (unsigned)clock();
+      bool progress = false;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        if (sl[k] >= 0 && now - stamp[k] >= age_cycles) {
+          // ---- centre, scale, convert, store, publish ----
+          const int s = first + sl[k];
+          const u64 p0 = ((u64)q[k][0].y << 32) | q[k][0].x, p1 = ((u64)q[k][0].w << 32) | q[k][0].z;  // x0 y0 | z0 x1
+          const u64 p2 = ((u64)q[k][1].y << 32) | q[k][1].x, p3 = ((u64)q[k][1].w << 32) | q[k][1].z;  // y1 z1 | x2 y2
+          const u64 p4 = ((u64)q[k][2].y << 32) | q[k][2].x, p5 = ((u64)q[k][2].w << 32) | q[k][2].z;  // z2 x3 | y3 z3
+          const float f0 = __uint_as_float(q[k][0].x), f1 = __uint_as_float(q[k][0].y), f2 = __uint_as_float(q[k][0].z);
+          const float cx = __shfl_sync(0xffffffffu, f0, src0), cy = __shfl_sync(0xffffffffu, f1, src0),
+                      cz = __shfl_sync(0xffffffffu, f2, src0);
+          const u64 cxy = pack2(cx, cy), czx = pack2(cz, cx), cyz = pack2(cy, cz);
+          const u64 e0 = sub2(p0, cxy), e1 = sub2(p1, czx), e2 = sub2(p2, cyz), e3 = sub2(p3, cxy), e4 = sub2(p4, czx),
+                    e5 = sub2(p5, cyz);
+          float m = fmaxf(fabsf(lo32(e0)), fabsf(hi32(e0)));
+          m = fmaxf(m, fmaxf(fabsf(lo32(e1)), fabsf(hi32(e1))));
+          m = fmaxf(m, fmaxf(fabsf(lo32(e2)), fabsf(hi32(e2))));
+          m = fmaxf(m, fmaxf(fabsf(lo32(e3)), fabsf(hi32(e3))));
+          m = fmaxf(m, fmaxf(fabsf(lo32(e4)), fabsf(hi32(e4))));
+          m = fmaxf(m, fmaxf(fabsf(lo32(e5)), fabsf(hi32(e5))));
+          const unsigned mb = act ? __float_as_uint(m) : 0u;  // non-negative floats order like their bit patterns
+          const unsigned r1 = __reduce_max_sync(0xffffffffu, second ? 0u : mb);
+          const unsigned r2 = __reduce_max_sync(0xffffffffu, second ? mb : 0u);
+          const float mm = __uint_as_float(second ? r2 : r1);
+          const bool ok = mm > 8.67361737988e-19f;  // 2^-60
+          const float sc = ok ? __fdividef(kS16Scale, mm) : 0.0f;
+          const u64 g0 = mul2s(e0, sc), g1v = mul2s(e1, sc), g2v = mul2s(e2, sc), g3 = mul2s(e3, sc), g4 = mul2s(e4, sc),
+                    g5 = mul2s(e5, sc);
+          // vertices: 0 = (g0.lo, g0.hi, g1.lo)  1 = (g1.hi, g2.lo, g2.hi)  2 = (g3.lo, g3.hi, g4.lo)  3 = (g4.hi, g5.lo, g5.hi)
+          const __half2 x01 = __floats2half2_rn(lo32(g0), hi32(g1v)), x23 = __floats2half2_rn(lo32(g3), hi32(g4));
+          const __half2 y01 = __floats2half2_rn(hi32(g0), lo32(g2v)), y23 = __floats2half2_rn(hi32(g3), lo32(g5));
+          const __half2 z01 = __floats2half2_rn(lo32(g1v), hi32(g2v)), z23 = __floats2half2_rn(lo32(g4), hi32(g5));
+          unsigned char* dst = slots + (size_t)s * sbytes;
+          if (act) {
+            *reinterpret_cast<uint2*>(dst + lane_off) =
+                make_uint2(*reinterpret_cast<const unsigned*>(&x01), *reinterpret_cast<const unsigned*>(&x23));
+            *reinterpret_cast<uint2*>(dst + lane_off + 16) =
+                make_uint2(*reinterpret_cast<const unsigned*>(&y01), *reinterpret_cast<const unsigned*>(&y23));
+            *reinterpret_cast<uint2*>(dst + lane_off + 32) =
+                make_uint2(*reinterpret_cast<const unsigned*>(&z01), *reinterpret_cast<const unsigned*>(&z23));
+          }
+          {  // header: c0 and W of this lane's body, stored by the lane that holds the first vertex
+            const float ws = kS16WCentre * sc;
+            const float w0 = ok ? fmaf(ws, fabsf(f0), kS16WConst) : 1e30f, w1 = ok ? fmaf(ws, fabsf(f1), kS16WConst) : 1e30f,
+                        w2 = ok ? fmaf(ws, fabsf(f2), kS16WConst) : 1e30f;
+            if (act && lg == 0) {
+              float2* hd = reinterpret_cast<float2*>(dst + (second ? 24 : 0));
+              hd[0] = make_float2(f0, f1);
+              hd[1] = make_float2(f2, w0);
+              hd[2] = make_float2(w1, w2);
+            }
+          }
+          if (lane == 0) {
+            pair_of[s] = tk[k];
+            if (IDX) {
+              idx1_of[s] = ri1[k];
+              idx2_of[s] = ri2[k];
+            }
+          }
+          __syncwarp();                                    // every lane's stores are ordered before ...
+          if (lane == 0) mbar_arrive(smem_addr(&bars[s]));  // ... the release that completes the slot's phase
+          busy &= ~(1u << sl[k]);
+          sl[k] = -1;
+          progress = true;
+        }
+        // ---- take a free slot of this warp's range, draw its ticket, issue its loads ----
+        if (sl[k] < 0 && fm && tk_next != tk_end) {
+          const int s = __ffs((int)fm) - 1;
+          fm &= fm - 1u;
+          stamp[k] = now;
+          const unsigned t = tk_next++;
+          if (t < n) {
+            int a = (int)t, b = (int)t;
+            if (IDX) {
+              a = __shfl_sync(0xffffffffu, rec1, (int)(t - tk_base));
+              b = __shfl_sync(0xffffffffu, rec2, (int)(t - tk_base));
+            }
+            if (lane == 0) st_vol(&ctrl[first + s], kS16Busy);
+            busy |= 1u << s;
+            sl[k] = s;
+            tk[k] = t;
+            ri1[k] = a;
+            ri2[k] = b;
+            if (act) {
+              const float* src = lane_src + (second ? (size_t)b * kBodyFloats2 : (size_t)a * kBodyFloats1);
+              q[k][0] = ldg128(src);
+              q[k][1] = ldg128(src + 4);
+              q[k][2] = ldg128(src + 8);
+            }
+          } else {  // out of work: the slot's owner may leave
+            if (lane == 0) st_vol(&ctrl[first + s], kS16Exit);
+            ++exited;
+          }
+          progress = true;
+        }
+      }
+      if (exited == 32) break;
+      // nothing to convert, nothing free: the owners hold a second, already filled slot each, so a lazy poll costs no
+      // throughput -- and a busy one would take the issue slots of the compute warps (the schedulers favour higher warp ids)
+      if (!progress) __nanosleep(idle_ns);
     }
   } else {
     // ================================================ finisher ===============================================
-    float* mine = scratch + lane * kS16ScratchWords;
     unsigned cur = 0;
     for (;;) {
       const unsigned idx = cur + lane;
@@ -499,8 +546,8 @@ gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ c
       const unsigned m = __ballot_sync(0xffffffffu, rdy);
       const int c = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);  // records ready in order from `cur`
       if (c == 0) {
-        if (ld_vol(&ring_ctl[2]) == (unsigned)CW && ld_vol(&ring_ctl[0]) == cur) break;
-        __nanosleep(100);
+        if (ld_vol(&ring_ctl[2]) == (unsigned)(CW / kS16Finishers) && ld_vol(&ring_ctl[0]) == cur) break;
+        __nanosleep(idle_ns / 2u);
         continue;
       }
       __threadfence_block();
@@ -529,15 +576,16 @@ gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ c
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) mine[6 * k + cc] = vt[k][cc];
           // the simplex point is the same fp32 subtraction the compute thread made when the vertex pair was added
           sv[k]->p = mk<T>(sub_rn(vt[k][0], vt[k][3]), sub_rn(vt[k][1], vt[k][4]), sub_rn(vt[k][2], vt[k][5]));
-          // tag (bits 30..31): which scratch entry this slot came with -- survives the witness stage's slot shuffles
+          // tag (bits 30..31): which fetched vertex pair this slot came with -- survives the witness stage's slot shuffles
           sv[k]->i1 = (int)((unsigned)vi[k][0] | ((unsigned)k << 30));
           sv[k]->i2 = (int)((unsigned)vi[k][1] | ((unsigned)k << 30));
         }
-        RecordFetch<T> fetch{mine};
+        const RegFetch16 fetch{{{vt[0][0], vt[0][1], vt[0][2], vt[0][3], vt[0][4], vt[0][5]},
+                                {vt[1][0], vt[1][1], vt[1][2], vt[1][3], vt[1][4], vt[1][5]},
+                                {vt[2][0], vt[2][1], vt[2][2], vt[2][3], vt[2][4], vt[2][5]},
+                                {vt[3][0], vt[3][1], vt[3][2], vt[3][3], vt[3][4], vt[3][5]}}};
         V3<T> w1, w2;
         gjk_witnesses(fetch, g.S, w1, w2);
 #pragma unroll

@@ -352,7 +352,7 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const T* c1, int nv2, const T* c2, Si
 // ---- fp16 pre-scan slot kernel (gjk_slots16.cuh): fp32 batches whose bodies have 8 * NB vertices, NB in 4..8 ---------
 // Takes over from the warp-specialised fp32-slot kernel wherever that one is down to 128 slots per SM (one compute warp
 // per scheduler).  OGJK_GJK_KERNEL=slots16 forces it for every supported shape, =slotsws32 keeps the fp32 slots;
-// OGJK_S16_CFG=<NC><P> (development) picks another converter configuration for the 64+64-vertex dense instance.
+// OGJK_S16_CFG=<D> (development) picks another converter ring depth for the 64+64-vertex dense instance.
 bool slots16_shape(int nv1, int nv2) { return nv1 == nv2 && nv1 % 8 == 0 && nv1 >= 32 && nv1 <= 64; }
 bool use_slots16(int nv1, int nv2, int esize) {
   if (esize != 4 || !slots16_shape(nv1, nv2)) return false;
@@ -362,7 +362,7 @@ bool use_slots16(int nv1, int nv2, int esize) {
   int lp = 1;
   return ws_config(nv1, nv2, &lp, esize) == 4;  // 128 fp32 slots: 40..64 vertices per body
 }
-template <int NB, bool IDX, int NC, int P>
+template <int NB, bool IDX, int D>
 int launch_gjk_slots16_inst(int n, const float* c1, const float* c2, SimplexT<float>* simp, float* dist, float* nrm,
                             int* queue, int* count, const CollisionPair* pairs) {
   const uint16_t* utab = nullptr;
@@ -371,29 +371,32 @@ int launch_gjk_slots16_inst(int n, const float* c1, const float* c2, SimplexT<fl
   if (int rc = ticket_buffer(&ticket)) return rc;
   constexpr size_t smem = s16_smem_bytes(NB, NB);
   static_assert(smem <= 227u * 1024u, "slots do not fit");
-  constexpr int threads = (kS16ComputeWarps + NC + 1) * 32;
-  auto kern = gjk_slots16_kernel<NB, NB, IDX, NC, P>;
+  auto kern = gjk_slots16_kernel<NB, NB, IDX, D>;
   long long grid = 0;
-  if (int rc = persistent_grid(kern, threads, smem, &grid)) return rc;
+  if (int rc = persistent_grid(kern, kS16Threads, smem, &grid)) return rc;
   const long long need = ((long long)n + kS16Slots - 1) / kS16Slots;
   if (grid > need) grid = need;
   OGJK_CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned), t_stream));
-  kern<<<(unsigned)grid, threads, smem, t_stream>>>(c1, c2, simp, dist, (unsigned)n, utab, ticket, nrm, queue, count, pairs);
+  const char* ie = getenv("OGJK_S16_IDLE");  // development: idle back-off of the converter warps in ns
+  const unsigned idle_ns = ie ? (unsigned)atoi(ie) : 200u;
+  const char* ae = getenv("OGJK_S16_AGE");  // development: age (SM cycles) at which a fetched pair is converted
+  const unsigned age = ae ? (unsigned)atoi(ae) : 3000u;
+  kern<<<(unsigned)grid, kS16Threads, smem, t_stream>>>(c1, c2, simp, dist, (unsigned)n, utab, ticket, nrm, queue, count, pairs,
+                                                        idle_ns, age);
   return finish_launch("gjk slots (fp16 pre-scan) kernel");
 }
 template <int NB>
 int launch_gjk_slots16_nb(int n, const float* c1, const float* c2, SimplexT<float>* simp, float* dist, float* nrm,
                           int* queue, int* count, const CollisionPair* pairs) {
-  if (pairs) return launch_gjk_slots16_inst<NB, true, 4, 6>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+  if (pairs) return launch_gjk_slots16_inst<NB, true, 4>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
   if constexpr (NB == 8) {
-    const char* e = getenv("OGJK_S16_CFG");
+    const char* e = getenv("OGJK_S16_CFG");  // development: depth of the converters' register ring
     const int cfg = e ? atoi(e) : 0;
-    if (cfg == 44) return launch_gjk_slots16_inst<NB, false, 4, 4>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
-    if (cfg == 48) return launch_gjk_slots16_inst<NB, false, 4, 8>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
-    if (cfg == 83) return launch_gjk_slots16_inst<NB, false, 8, 3>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
-    if (cfg == 84) return launch_gjk_slots16_inst<NB, false, 8, 4>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+    if (cfg == 2) return launch_gjk_slots16_inst<NB, false, 2>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+    if (cfg == 3) return launch_gjk_slots16_inst<NB, false, 3>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+    if (cfg == 5) return launch_gjk_slots16_inst<NB, false, 5>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
   }
-  return launch_gjk_slots16_inst<NB, false, 4, 6>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
+  return launch_gjk_slots16_inst<NB, false, 4>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
 }
 int launch_gjk_slots16(int n, int nv, const float* c1, const float* c2, SimplexT<float>* simp, float* dist, float* nrm,
                        int* queue, int* count, const CollisionPair* pairs) {
