@@ -18,18 +18,19 @@
 // with it every later bit of the iteration -- is the reference's.  On the benchmark generator 1.19 vertices per scan
 // are candidates (83 % of the scans: one).
 //
-// Roles (one CTA per SM, 8 + 8 + 1 warps):
-//   * compute warps: ONE THREAD PER PAIR as in gjk_slots.cuh (rotated loop, lane-uniform iteration gjk_substep_u);
-//   * converter warps replace the TMA loader, one per compute warp: each polls the 32 slot flags of its compute warp,
-//     draws tickets, fetches a pair's two fp32 vertex sets with 128-bit loads (lane l: four consecutive vertices),
-//     centres / scales / converts them (packed FADD2 / FMUL2) and writes the fp16 slot in blocks of eight vertices
-//     x0..x7 | y0..y7 | z0..z7  (three 128-bit shared loads per block in the scan).  The loads of D pairs rotate
-//     through a register ring, so D - 1 pairs per converter warp are in flight while one is converted: the bytes in
-//     flight that the TMA version kept in idle slots are held in the converters' registers.  A converted slot is
-//     published with an mbarrier arrive (release) -- no memory fence, which would wait for the loads in flight;
-//   * the finisher warp takes 9-word records (pair, simplex size, v, vertex indices), re-reads the <= 8 source vertices
-//     from global memory/L2, rebuilds the simplex points (the same fp32 subtraction), and runs the witness stage, the
-//     result stores and the fused EPA gate exactly as in gjk_slots.cuh.
+// Roles (one CTA per SM, 8 + 2 warps):
+//   * compute warps: ONE THREAD PER PAIR as in gjk_slots.cuh (rotated loop, lane-uniform iteration gjk_substep_u).  There
+//     is no loader: a warp refills its own slots.  At every half-trip it issues the 128-bit loads of up to K pairs for
+//     its free slots (lane l: four consecutive vertices of one body, three loads) into a register ring, and at the next
+//     half-trip all 32 lanes centre / scale / convert (packed FADD2 / FMUL2) those pairs and write their owners' fp16
+//     slots in blocks of eight vertices  x0..x7 | y0..y7 | z0..z7  (three 128-bit shared loads per block in the scan).
+//     The bytes in flight that the TMA version kept in idle slots are held in registers (8 warps x K pairs); producer
+//     and consumer of a slot are the same warp, so __syncwarp() is the only synchronisation -- no flags, no mbarriers,
+//     no polling, and ONE instruction stream for fetching, converting and iterating (a version with separate
+//     converter warps was instruction-fetch bound: profiles/r2_experiments.txt);
+//   * two finisher warps (four compute warps each) take 9-word records (pair, simplex size, v, vertex indices), re-read
+//     the <= 8 source vertices from global memory/L2, rebuild the simplex points (the same fp32 subtraction), and run
+//     the witness stage, the result stores and the fused EPA gate exactly as in gjk_slots.cuh.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -38,11 +39,10 @@
 namespace ogjk {
 
 constexpr int kS16Slots = 256;
-constexpr int kS16ComputeWarps = 4;   // 128 threads, TWO slots each: one being worked on, one being refilled
+constexpr int kS16ComputeWarps = 8;   // one slot per thread
 constexpr int kS16RingRecords = 64;
 constexpr int kS16RecWords = 9;       // pair | n | v.xyz | polytope index 1 | polytope index 2 | vertex indices (2 words)
-constexpr int kS16Finishers = 2;      // finisher f serves compute warps 2 f and 2 f + 1 through its own record ring
-enum : unsigned { kS16Free = 0u, kS16Busy = 1u, kS16Exit = 2u };
+constexpr int kS16Finishers = 2;      // finisher f serves compute warps 4 f .. 4 f + 3 through its own record ring
 constexpr float kS16Scale = 16000.0f;
 constexpr float kS16WConst = 86.1f;
 constexpr float kS16WCentre = 3.7e-7f;
@@ -55,8 +55,8 @@ __host__ __device__ constexpr uint32_t s16_slot_bytes(int nb1, int nb2) {
   return units * 16u;
 }
 __host__ __device__ constexpr uint32_t s16_fixed_bytes() {
-  // mbarriers | table | ctrl | pair_of | idx1_of | idx2_of | per finisher: ring control (16 B), ready flags, ring
-  return (uint32_t)kS16Slots * 8u + kSlotTableBytes + (uint32_t)kS16Slots * 16u +
+  // table | per finisher: ring control (16 B), ready flags, ring
+  return kSlotTableBytes +
          (uint32_t)kS16Finishers * (16u + (uint32_t)kS16RingRecords * 4u + (((uint32_t)kS16RingRecords * kS16RecWords * 4u + 15u) & ~15u));
 }
 __host__ __device__ constexpr uint32_t s16_smem_bytes(int nb1, int nb2) {
@@ -184,46 +184,31 @@ OGJK_D unsigned atom_add_global(unsigned* p, unsigned v) {  // one ATOMG, withou
 }
 OGJK_D float lo32(u64 a) { return __uint_as_float((unsigned)a); }
 OGJK_D float hi32(u64 a) { return __uint_as_float((unsigned)(a >> 32)); }
-OGJK_D void mbar_arrive(uint32_t bar) {  // release at CTA scope: the slot's stores are visible to the waiting thread
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
-// NB1 / NB2: blocks of eight vertices per body (vertex counts 8 NB1 and 8 NB2, 2 (NB1 + NB2) <= 32 converter lanes).
-// IDX: pairs are gkCollisionPair records into one pool.  D: depth of the converters' register ring (pairs per warp).
-constexpr int kS16Converters = kS16Slots / 32;  // converter c serves slots 32 c .. 32 c + 31
-constexpr int kS16Threads = (kS16ComputeWarps + kS16Converters + kS16Finishers) * 32;
-template <int NB1, int NB2, bool IDX, int D>
+// NB1 / NB2: blocks of eight vertices per body (vertex counts 8 NB1 and 8 NB2, 2 (NB1 + NB2) <= 32 converting lanes).
+// IDX: pairs are gkCollisionPair records into one pool.  K: pairs a warp keeps in flight (register ring).
+constexpr int kS16Threads = (kS16ComputeWarps + kS16Finishers) * 32;
+template <int NB1, int NB2, bool IDX, int K>
 __global__ void __launch_bounds__(kS16Threads)
 gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ coord2, SimplexT<float>* __restrict__ simplices,
                    float* __restrict__ distances, unsigned n, const uint16_t* __restrict__ utab_g,
                    unsigned* __restrict__ ticket, float* __restrict__ normals, int* __restrict__ epa_queue,
-                   int* __restrict__ epa_count, const CollisionPair* __restrict__ pairs, unsigned idle_ns, unsigned age_cycles) {
+                   int* __restrict__ epa_count, const CollisionPair* __restrict__ pairs) {
   typedef float T;
   constexpr int CW = kS16ComputeWarps;
-  constexpr int NC = kS16Converters;
   constexpr int kThreads = kS16Threads;
   constexpr int NV1 = 8 * NB1, NV2 = 8 * NB2;
-  constexpr int G1 = 2 * NB1, G2 = 2 * NB2;  // converter lanes per body (four vertices each)
-  static_assert(G1 + G2 <= 32, "a pair must fit the 32 lanes of a converter warp");
+  constexpr int G1 = 2 * NB1, G2 = 2 * NB2;  // converting lanes per body (four vertices each)
+  static_assert(G1 + G2 <= 32, "a pair must fit the 32 lanes of a warp");
   constexpr uint32_t sbytes = s16_slot_bytes(NB1, NB2);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* sp = smem_raw;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sp);  // one mbarrier per slot: completed by the converter's arrive
-  sp += kS16Slots * 8;
   uint16_t* utab = reinterpret_cast<uint16_t*>(sp);
   sp += kSlotTableBytes;
-  unsigned* ctrl = reinterpret_cast<unsigned*>(sp);
-  sp += kS16Slots * 4;
-  unsigned* pair_of = reinterpret_cast<unsigned*>(sp);
-  sp += kS16Slots * 4;
-  int* idx1_of = reinterpret_cast<int*>(sp);
-  sp += kS16Slots * 4;
-  int* idx2_of = reinterpret_cast<int*>(sp);
-  sp += kS16Slots * 4;
-  // record rings: compute warps 0 and 1 feed finisher 0, warps 2 and 3 finisher 1
+  // record rings: compute warps 0..3 feed finisher 0, warps 4..7 finisher 1
   constexpr uint32_t kRingBytes = 16u + kS16RingRecords * 4u + ((kS16RingRecords * kS16RecWords * 4u + 15u) & ~15u);
-  const int fin_id = warp < CW ? warp / (CW / kS16Finishers) : (warp >= CW + NC ? warp - CW - NC : 0);
+  const int fin_id = warp < CW ? warp / (CW / kS16Finishers) : warp - CW;
   unsigned* ring_ctl = reinterpret_cast<unsigned*>(sp + fin_id * kRingBytes);  // [0] tail (reserved), [1] head (consumed), [2] exited warps
   unsigned* ready = ring_ctl + 4;
   unsigned* ring = ready + kS16RingRecords;
@@ -231,182 +216,61 @@ gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ c
 
   for (int i = tid; i < kUnifiedSize / 2; i += kThreads)
     reinterpret_cast<uint32_t*>(utab)[i] = __ldg(reinterpret_cast<const uint32_t*>(utab_g) + i);
-  for (int i = tid; i < kS16Slots; i += kThreads) {
-    mbar_init(smem_addr(&bars[i]), 1);
-    ctrl[i] = kS16Free;
-    pair_of[i] = 0;
-  }
   for (int i = tid; i < (int)(kS16Finishers * kRingBytes / 4u); i += kThreads) reinterpret_cast<unsigned*>(sp)[i] = 0;
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
   if (warp < CW) {
-    // ================================================ compute ================================================
-    // slot b of this thread is slot b * 128 + tid: while the pair in one is iterated, the converters refill the other,
-    // so a finished pair is followed by the next one without waiting for memory
-    int cur = 0;            // the buffer in use (or waited for)
-    uint32_t parities = 0;  // bit b: phase parity of buffer b's mbarrier
-    unsigned gone = 0;      // bit b: buffer b has been told to exit
-    int cslot = tid;
-    const float* hdr = reinterpret_cast<const float*>(slots + (size_t)cslot * sbytes);
-    const uint4* blk1 = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(hdr) + kS16HeaderBytes);
+    // =================================== compute + conversion (one code stream) ===================================
+    // Lane l owns slot 32 warp + l for every phase of its pair; the warp as a whole fetches and converts the pairs of
+    // its own free slots: at the top of a half-trip a pair's two fp32 vertex sets are requested with three 128-bit loads
+    // per lane (lane l: four consecutive vertices) into K register sets, and at the bottom -- behind the half-trip's
+    // arithmetic, which is what hides the latency -- they are centred / scaled / converted / stored into the owner's
+    // slot.  K pairs per warp are in flight (the bytes in flight that the TMA version kept in idle slots are held in
+    // registers), and no flag, barrier or polling warp is involved: producer and consumer are the same warp,
+    // __syncwarp() orders the slot stores.  (Loads and conversion sit in ONE loop iteration on purpose: across the
+    // back-edge ptxas waits for every outstanding load at the loop top, profiles/r2_experiments.txt.)
+    const unsigned char* sbase = slots + (size_t)tid * sbytes;
+    const float* hdr = reinterpret_cast<const float*>(sbase);
+    const uint4* blk1 = reinterpret_cast<const uint4*>(sbase + kS16HeaderBytes);
     const uint4* blk2 = blk1 + 3 * NB1;
-    auto other_buffer = [&]() {  // switch to the other buffer unless it has been told to exit
-      if ((gone >> (cur ^ 1)) & 1u) return;
-      cur ^= 1;
-      cslot = cur * (CW * 32) + tid;
-      hdr = reinterpret_cast<const float*>(slots + (size_t)cslot * sbytes);
-      blk1 = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(hdr) + kS16HeaderBytes);
-      blk2 = blk1 + 3 * NB1;
-    };
-    enum { kWait = 0, kRun = 1, kExit = 2 };
-    int state = kWait;
+    unsigned char* const wslots = slots + (size_t)(warp * 32) * sbytes;  // this warp's 32 slots
+    // conversion role of this lane
+    const bool second = lane >= G1;  // four vertices of body 2
+    const bool act = lane < G1 + G2;
+    const int lg = second ? lane - G1 : lane;  // 4-vertex group within the body
+    const int src0 = second ? G1 : 0;          // lane holding the body's first vertex
+    const uint32_t lane_off = kS16HeaderBytes + (uint32_t)(second ? NB1 * 48 : 0) + (uint32_t)(lg >> 1) * 48u + (uint32_t)(lg & 1) * 8u;
+    const float* const lane_src = (second ? coord2 : coord1) + (act ? lg : 0) * 12;  // idle lanes re-read group 0
+    constexpr int kBodyFloats1 = NV1 * 3, kBodyFloats2 = NV2 * 3;
+    // tickets (warp-uniform): the range in use [tk_next, tk_end) and a spare [sp_next, sp_end) requested with one atomic
+    // and collected a half-trip later, together with -- for indexed batches -- the range's pair records (one per lane)
+    unsigned tk_next = 0, tk_end = 0, tk_base = 0, sp_next = 0, sp_end = 0;
+    unsigned raw = 0;  // lane 0: result of the atomic in flight
+    bool pending = false;
+    int rec1 = 0, rec2 = 0, srec1 = 0, srec2 = 0;
+    // the register ring
+    ulonglong2 q[K][3];  // x0 y0 | z0 x1 || y1 z1 | x2 y2 || z2 x3 | y3 z3
+    int sl[K];
+    unsigned tk[K];
+    int ri1[K], ri2[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) sl[k] = -1;
+    unsigned freemask = 0xffffffffu;  // slots waiting for a pair (warp-uniform)
+    unsigned exitmask = 0;            // slots that were told there is no more work
+    enum { kIdle = 0, kFresh = 1, kRun = 2 };
+    int state = kIdle;
     unsigned pair = 0;
     int pi1 = 0, pi2 = 0;
     const float* g1 = coord1;  // this pair's fp32 vertices in global memory
     const float* g2 = coord2;
     GjkState<T> g;
-    bool need_sub = false;  // rotated loop, see gjk_slots_ws_kernel
-    for (;;) {
-      bool fin_sub = false;
-      if (state == kRun && need_sub) fin_sub = gjk_substep_u(g, utab);
-      need_sub = false;
-      if (state == kWait) {
-        if (mbar_test_wait(smem_addr(&bars[cslot]), (parities >> cur) & 1u)) {  // acquire: the converter's stores
-          parities ^= 1u << cur;
-          pair = ld_vol(&pair_of[cslot]);
-          pi1 = pi2 = (int)pair;
-          if (IDX) {
-            pi1 = *reinterpret_cast<volatile int*>(&idx1_of[cslot]);
-            pi2 = *reinterpret_cast<volatile int*>(&idx2_of[cslot]);
-          }
-          g1 = coord1 + (size_t)pi1 * (NV1 * 3);
-          g2 = coord2 + (size_t)pi2 * (NV2 * 3);
-          gjk_init(g, mk<T>(hdr[0], hdr[1], hdr[2]), mk<T>(hdr[6], hdr[7], hdr[8]));
-          state = kRun;
-        } else if (ld_vol(&ctrl[cslot]) == kS16Exit) {  // no more work for this buffer: leave when both have been told
-          gone |= 1u << cur;
-          if (gone == 3u) state = kExit;
-        }
-        if (state == kWait) other_buffer();  // not ready: look at the other buffer next trip
-      }
-      if (__all_sync(0xffffffffu, state == kExit)) break;
-      if (!__any_sync(0xffffffffu, state == kRun)) __nanosleep(32);  // start-up / drain
-      bool finished = fin_sub;
-      if (state == kRun && !fin_sub) {
-        ++g.k;
-        // ---- pre-scan of both bodies over the fp16 slot ----
-        const Dir16 D = make_dir16(g.v);
-        const __half2 nx = __hneg2(D.x), ny = __hneg2(D.y), nz = __hneg2(D.z);
-        const float s1 = fmaf(D.qx, hdr[3], fmaf(D.qy, hdr[4], D.qz * hdr[5])) * 1.000244140625f + 0.5f;
-        const float s2 = fmaf(D.qx, hdr[9], fmaf(D.qy, hdr[10], D.qz * hdr[11])) * 1.000244140625f + 0.5f;
-        Cand16 c1, c2;
-        __half2 thr1, thr2;
-        prescan16<NB1>(blk1, nx, ny, nz, s1, D.wide, c1, thr1);
-        prescan16<NB2>(blk2, D.x, D.y, D.z, s2, D.wide, c2, thr2);
-        // ---- exact verification of the candidates, the reference's scan restricted to them ----
-        const V3<T> nvv = vneg(g.v);
-        T best1 = dot(g.sup1, nvv), best2 = dot(g.sup2, g.v);
-        while ((c1.blocks | c1.verts | c2.blocks | c2.verts) != 0u) {
-          const int i1 = next_candidate16(c1, blk1, nx, ny, nz, thr1, D.wide);
-          const int i2 = next_candidate16(c2, blk2, D.x, D.y, D.z, thr2, D.wide);
-          V3<T> p = g.sup1, q = g.sup2;
-          if (i1 >= 0) {
-            const float* a = g1 + 3 * i1;
-            p = mk<T>(__ldg(a), __ldg(a + 1), __ldg(a + 2));
-          }
-          if (i2 >= 0) {
-            const float* a = g2 + 3 * i2;
-            q = mk<T>(__ldg(a), __ldg(a + 1), __ldg(a + 2));
-          }
-          if (i1 >= 0) {
-            const T dd = dot(p, nvv);
-            if (dd > best1) {
-              best1 = dd;
-              g.sup1 = p;
-              g.idx1 = i1;
-            }
-          }
-          if (i2 >= 0) {
-            const T dd = dot(q, g.v);
-            if (dd > best2) {
-              best2 = dd;
-              g.sup2 = q;
-              g.idx2 = i2;
-            }
-          }
-        }
-        finished = gjk_converged_u(g);
-        need_sub = !finished;
-      }
-      // ---- retire: 9-word record for the finisher, slot back to the converters ----
-      {
-        const unsigned fin = __ballot_sync(0xffffffffu, finished);
-        if (fin) {
-          const unsigned cnt = __popc(fin);
-          unsigned base = 0;
-          if (lane == 0) base = atomicAdd(&ring_ctl[0], cnt);
-          base = __shfl_sync(0xffffffffu, base, 0);
-          while ((int)(base + cnt - ld_vol(&ring_ctl[1])) > kS16RingRecords) __nanosleep(64);  // ring full
-          const unsigned idx = base + __popc(fin & ((1u << lane) - 1u));
-          if (finished) {
-            unsigned* rec = ring + (size_t)(idx % kS16RingRecords) * kS16RecWords;
-            rec[0] = pair;
-            rec[1] = (unsigned)g.S.n;
-            rec[2] = __float_as_uint(g.v.x);
-            rec[3] = __float_as_uint(g.v.y);
-            rec[4] = __float_as_uint(g.v.z);
-            rec[5] = (unsigned)pi1;
-            rec[6] = (unsigned)pi2;
-            rec[7] = (unsigned)g.S.s0.i1 | ((unsigned)g.S.s0.i2 << 8) | ((unsigned)g.S.s1.i1 << 16) | ((unsigned)g.S.s1.i2 << 24);
-            rec[8] = (unsigned)g.S.s2.i1 | ((unsigned)g.S.s2.i2 << 8) | ((unsigned)g.S.s3.i1 << 16) | ((unsigned)g.S.s3.i2 << 24);
-            __threadfence_block();  // record (and this thread's slot reads) before the two flags
-          }
-          __syncwarp();
-          if (finished) {
-            st_vol(&ready[idx % kS16RingRecords], idx / kS16RingRecords + 1u);
-            st_vol(&ctrl[cslot], kS16Free);
-            state = kWait;
-            other_buffer();  // refilled while this pair was iterated
-          }
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      atomicAdd(&ring_ctl[2], 1u);
-    }
-  } else if (warp < CW + NC) {
-    // =============================================== converter ===============================================
-    const int first = (warp - CW) * 32;  // this warp serves the 32 slots of compute warp (warp - CW)
-    const bool second = lane >= G1;      // this lane converts four vertices of body 2
-    const bool act = lane < G1 + G2;
-    const int lg = second ? lane - G1 : lane;  // 4-vertex group within the body
-    const int src0 = second ? G1 : 0;          // lane holding the body's first vertex
-    const uint32_t lane_off = kS16HeaderBytes + (uint32_t)(second ? NB1 * 48 : 0) + (uint32_t)(lg >> 1) * 48u + (uint32_t)(lg & 1) * 8u;
-    const float* const lane_src = (second ? coord2 : coord1) + lg * 12;
-    constexpr int kBodyFloats1 = NV1 * 3, kBodyFloats2 = NV2 * 3;
-    // tickets (warp-uniform state): the range in use [tk_next, tk_end) and a spare one [sp_next, sp_end) that is
-    // requested (one atomic by lane 0) and collected at the top of the ring loop, a whole pass apart, so that neither
-    // the atomic's round trip nor -- for indexed batches -- the load of the range's pair records is ever waited for
-    unsigned tk_next = 0, tk_end = 0, tk_base = 0, sp_next = 0, sp_end = 0;
-    unsigned raw = 0;  // lane 0: result of the atomic in flight
-    bool pending = false;
-    int rec1 = 0, rec2 = 0, srec1 = 0, srec2 = 0;  // IDX: this lane's pair record of the range in use / the spare range
-    unsigned busy = 0;       // slots picked but not yet published
-    int exited = 0;
-    // the register ring: up to D pairs whose loads are in flight.  An entry is converted once it is `age_cycles` old
-    // (about the latency of its loads): converting it earlier would block the warp on the scoreboard and with it the
-    // loads of the slots that fall free in the meantime
-    uint4 q[D][3];
-    unsigned stamp[D];
-    int sl[D];
-    unsigned tk[D];
-    int ri1[D], ri2[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) sl[k] = -1;
-    for (;;) {
+    bool need_sub = false;
+    // A trip is two half-trips: [sub-algorithm step of the iteration begun last trip | pre-scans + verification + the two
+    // exit pre-tests of the next iteration], each preceded by [request the vertices for the free slots] and followed by
+    // [retire the lanes that finished | convert what was requested].  The arithmetic per pair is the sequence of
+    // gjk_advance_u.
+    for (int phase = 0;; phase ^= 1) {
+      // ---- tickets: collect the spare range requested a half-trip ago, or request one ----
       if (sp_next == sp_end) {
         if (!pending) {
           if (lane == 0) raw = atom_add_global(ticket, kTicketChunk);
@@ -432,110 +296,187 @@ gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ c
         rec1 = srec1;
         rec2 = srec2;
       }
-      // free slots of this warp's range, looked at once per pass
-      unsigned fm = __ballot_sync(0xffffffffu, ld_vol(&ctrl[first + lane]) == kS16Free) & ~busy;
-      const unsigned now = (unsigned)clock();
-      bool progress = false;
+      // ---- fetch for the free slots: these registers are the bytes in flight ----
+      // (the loads are issued unconditionally -- from pair 0 when an entry stays empty -- so that the ring registers are
+      //  written by the loads alone: a conditional assignment makes the compiler wait for the load right here)
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        if (sl[k] >= 0 && now - stamp[k] >= age_cycles) {
-          // ---- centre, scale, convert, store, publish ----
-          const int s = first + sl[k];
-          const u64 p0 = ((u64)q[k][0].y << 32) | q[k][0].x, p1 = ((u64)q[k][0].w << 32) | q[k][0].z;  // x0 y0 | z0 x1
-          const u64 p2 = ((u64)q[k][1].y << 32) | q[k][1].x, p3 = ((u64)q[k][1].w << 32) | q[k][1].z;  // y1 z1 | x2 y2
-          const u64 p4 = ((u64)q[k][2].y << 32) | q[k][2].x, p5 = ((u64)q[k][2].w << 32) | q[k][2].z;  // z2 x3 | y3 z3
-          const float f0 = __uint_as_float(q[k][0].x), f1 = __uint_as_float(q[k][0].y), f2 = __uint_as_float(q[k][0].z);
-          const float cx = __shfl_sync(0xffffffffu, f0, src0), cy = __shfl_sync(0xffffffffu, f1, src0),
-                      cz = __shfl_sync(0xffffffffu, f2, src0);
-          const u64 cxy = pack2(cx, cy), czx = pack2(cz, cx), cyz = pack2(cy, cz);
-          const u64 e0 = sub2(p0, cxy), e1 = sub2(p1, czx), e2 = sub2(p2, cyz), e3 = sub2(p3, cxy), e4 = sub2(p4, czx),
-                    e5 = sub2(p5, cyz);
-          float m = fmaxf(fabsf(lo32(e0)), fabsf(hi32(e0)));
-          m = fmaxf(m, fmaxf(fabsf(lo32(e1)), fabsf(hi32(e1))));
-          m = fmaxf(m, fmaxf(fabsf(lo32(e2)), fabsf(hi32(e2))));
-          m = fmaxf(m, fmaxf(fabsf(lo32(e3)), fabsf(hi32(e3))));
-          m = fmaxf(m, fmaxf(fabsf(lo32(e4)), fabsf(hi32(e4))));
-          m = fmaxf(m, fmaxf(fabsf(lo32(e5)), fabsf(hi32(e5))));
-          const unsigned mb = act ? __float_as_uint(m) : 0u;  // non-negative floats order like their bit patterns
-          const unsigned r1 = __reduce_max_sync(0xffffffffu, second ? 0u : mb);
-          const unsigned r2 = __reduce_max_sync(0xffffffffu, second ? mb : 0u);
-          const float mm = __uint_as_float(second ? r2 : r1);
-          const bool ok = mm > 8.67361737988e-19f;  // 2^-60
-          const float sc = ok ? __fdividef(kS16Scale, mm) : 0.0f;
-          const u64 g0 = mul2s(e0, sc), g1v = mul2s(e1, sc), g2v = mul2s(e2, sc), g3 = mul2s(e3, sc), g4 = mul2s(e4, sc),
-                    g5 = mul2s(e5, sc);
-          // vertices: 0 = (g0.lo, g0.hi, g1.lo)  1 = (g1.hi, g2.lo, g2.hi)  2 = (g3.lo, g3.hi, g4.lo)  3 = (g4.hi, g5.lo, g5.hi)
-          const __half2 x01 = __floats2half2_rn(lo32(g0), hi32(g1v)), x23 = __floats2half2_rn(lo32(g3), hi32(g4));
-          const __half2 y01 = __floats2half2_rn(hi32(g0), lo32(g2v)), y23 = __floats2half2_rn(hi32(g3), lo32(g5));
-          const __half2 z01 = __floats2half2_rn(lo32(g1v), hi32(g2v)), z23 = __floats2half2_rn(lo32(g4), hi32(g5));
-          unsigned char* dst = slots + (size_t)s * sbytes;
-          if (act) {
-            *reinterpret_cast<uint2*>(dst + lane_off) =
-                make_uint2(*reinterpret_cast<const unsigned*>(&x01), *reinterpret_cast<const unsigned*>(&x23));
-            *reinterpret_cast<uint2*>(dst + lane_off + 16) =
-                make_uint2(*reinterpret_cast<const unsigned*>(&y01), *reinterpret_cast<const unsigned*>(&y23));
-            *reinterpret_cast<uint2*>(dst + lane_off + 32) =
-                make_uint2(*reinterpret_cast<const unsigned*>(&z01), *reinterpret_cast<const unsigned*>(&z23));
-          }
-          {  // header: c0 and W of this lane's body, stored by the lane that holds the first vertex
-            const float ws = kS16WCentre * sc;
-            const float w0 = ok ? fmaf(ws, fabsf(f0), kS16WConst) : 1e30f, w1 = ok ? fmaf(ws, fabsf(f1), kS16WConst) : 1e30f,
-                        w2 = ok ? fmaf(ws, fabsf(f2), kS16WConst) : 1e30f;
-            if (act && lg == 0) {
-              float2* hd = reinterpret_cast<float2*>(dst + (second ? 24 : 0));
-              hd[0] = make_float2(f0, f1);
-              hd[1] = make_float2(f2, w0);
-              hd[2] = make_float2(w1, w2);
-            }
-          }
-          if (lane == 0) {
-            pair_of[s] = tk[k];
-            if (IDX) {
-              idx1_of[s] = ri1[k];
-              idx2_of[s] = ri2[k];
-            }
-          }
-          __syncwarp();                                    // every lane's stores are ordered before ...
-          if (lane == 0) mbar_arrive(smem_addr(&bars[s]));  // ... the release that completes the slot's phase
-          busy &= ~(1u << sl[k]);
-          sl[k] = -1;
-          progress = true;
+      for (int k = 0; k < K; ++k) {
+        const bool have = freemask != 0u && tk_next != tk_end;  // warp-uniform
+        const int s = have ? __ffs((int)freemask) - 1 : 0;
+        const unsigned t = have ? tk_next : 0u;
+        const bool take = have && t < n;
+        if (have) {
+          freemask &= freemask - 1u;
+          ++tk_next;
+          if (!take) exitmask |= 1u << s;  // out of work
         }
-        // ---- take a free slot of this warp's range, draw its ticket, issue its loads ----
-        if (sl[k] < 0 && fm && tk_next != tk_end) {
-          const int s = __ffs((int)fm) - 1;
-          fm &= fm - 1u;
-          stamp[k] = now;
-          const unsigned t = tk_next++;
-          if (t < n) {
-            int a = (int)t, b = (int)t;
-            if (IDX) {
-              a = __shfl_sync(0xffffffffu, rec1, (int)(t - tk_base));
-              b = __shfl_sync(0xffffffffu, rec2, (int)(t - tk_base));
+        int a = (int)t, b = (int)t;
+        if (IDX) {
+          a = __shfl_sync(0xffffffffu, rec1, (int)((t - tk_base) & 31u));
+          b = __shfl_sync(0xffffffffu, rec2, (int)((t - tk_base) & 31u));
+        }
+        if (!take) a = b = 0;
+        sl[k] = take ? s : -1;
+        tk[k] = t;
+        ri1[k] = a;
+        ri2[k] = b;
+        const float* src = lane_src + (second ? (size_t)b * kBodyFloats2 : (size_t)a * kBodyFloats1);
+        q[k][0] = __ldg(reinterpret_cast<const ulonglong2*>(src));
+        q[k][1] = __ldg(reinterpret_cast<const ulonglong2*>(src + 4));
+        q[k][2] = __ldg(reinterpret_cast<const ulonglong2*>(src + 8));
+      }
+      bool finished = false;
+      if (phase == 0) {
+        if (state == kRun && need_sub) finished = gjk_substep_u(g, utab);
+        need_sub = false;
+      } else {
+        if (state == kFresh) {  // converted at the last half-trip
+          g1 = coord1 + (size_t)pi1 * (NV1 * 3);
+          g2 = coord2 + (size_t)pi2 * (NV2 * 3);
+          gjk_init(g, mk<T>(hdr[0], hdr[1], hdr[2]), mk<T>(hdr[6], hdr[7], hdr[8]));
+          state = kRun;
+        }
+        if (state == kRun) {
+          ++g.k;
+          // ---- pre-scan of both bodies over the fp16 slot ----
+          const Dir16 D = make_dir16(g.v);
+          const __half2 nx = __hneg2(D.x), ny = __hneg2(D.y), nz = __hneg2(D.z);
+          const float s1 = fmaf(D.qx, hdr[3], fmaf(D.qy, hdr[4], D.qz * hdr[5])) * 1.000244140625f + 0.5f;
+          const float s2 = fmaf(D.qx, hdr[9], fmaf(D.qy, hdr[10], D.qz * hdr[11])) * 1.000244140625f + 0.5f;
+          Cand16 c1, c2;
+          __half2 thr1, thr2;
+          prescan16<NB1>(blk1, nx, ny, nz, s1, D.wide, c1, thr1);
+          prescan16<NB2>(blk2, D.x, D.y, D.z, s2, D.wide, c2, thr2);
+          // ---- exact verification of the candidates, the reference's scan restricted to them ----
+          const V3<T> nvv = vneg(g.v);
+          T best1 = dot(g.sup1, nvv), best2 = dot(g.sup2, g.v);
+          while ((c1.blocks | c1.verts | c2.blocks | c2.verts) != 0u) {
+            const int i1 = next_candidate16(c1, blk1, nx, ny, nz, thr1, D.wide);
+            const int i2 = next_candidate16(c2, blk2, D.x, D.y, D.z, thr2, D.wide);
+            V3<T> p = g.sup1, qq = g.sup2;
+            if (i1 >= 0) {
+              const float* a = g1 + 3 * i1;
+              p = mk<T>(__ldg(a), __ldg(a + 1), __ldg(a + 2));
             }
-            if (lane == 0) st_vol(&ctrl[first + s], kS16Busy);
-            busy |= 1u << s;
-            sl[k] = s;
-            tk[k] = t;
-            ri1[k] = a;
-            ri2[k] = b;
-            if (act) {
-              const float* src = lane_src + (second ? (size_t)b * kBodyFloats2 : (size_t)a * kBodyFloats1);
-              q[k][0] = ldg128(src);
-              q[k][1] = ldg128(src + 4);
-              q[k][2] = ldg128(src + 8);
+            if (i2 >= 0) {
+              const float* a = g2 + 3 * i2;
+              qq = mk<T>(__ldg(a), __ldg(a + 1), __ldg(a + 2));
             }
-          } else {  // out of work: the slot's owner may leave
-            if (lane == 0) st_vol(&ctrl[first + s], kS16Exit);
-            ++exited;
+            if (i1 >= 0) {
+              const T dd = dot(p, nvv);
+              if (dd > best1) {
+                best1 = dd;
+                g.sup1 = p;
+                g.idx1 = i1;
+              }
+            }
+            if (i2 >= 0) {
+              const T dd = dot(qq, g.v);
+              if (dd > best2) {
+                best2 = dd;
+                g.sup2 = qq;
+                g.idx2 = i2;
+              }
+            }
           }
-          progress = true;
+          finished = gjk_converged_u(g);
+          need_sub = !finished;
         }
       }
-      if (exited == 32) break;
-      // nothing to convert, nothing free: the owners hold a second, already filled slot each, so a lazy poll costs no
-      // throughput -- and a busy one would take the issue slots of the compute warps (the schedulers favour higher warp ids)
-      if (!progress) __nanosleep(idle_ns);
+      // ---- retire: 9-word record for the finisher; the slot joins the free list ----
+      {
+        const unsigned fin = __ballot_sync(0xffffffffu, finished);
+        if (fin) {
+          const unsigned cnt = __popc(fin);
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(&ring_ctl[0], cnt);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          while ((int)(base + cnt - ld_vol(&ring_ctl[1])) > kS16RingRecords) __nanosleep(64);  // ring full
+          const unsigned idx = base + __popc(fin & ((1u << lane) - 1u));
+          if (finished) {
+            unsigned* rec = ring + (size_t)(idx % kS16RingRecords) * kS16RecWords;
+            rec[0] = pair;
+            rec[1] = (unsigned)g.S.n;
+            rec[2] = __float_as_uint(g.v.x);
+            rec[3] = __float_as_uint(g.v.y);
+            rec[4] = __float_as_uint(g.v.z);
+            rec[5] = (unsigned)pi1;
+            rec[6] = (unsigned)pi2;
+            rec[7] = (unsigned)g.S.s0.i1 | ((unsigned)g.S.s0.i2 << 8) | ((unsigned)g.S.s1.i1 << 16) | ((unsigned)g.S.s1.i2 << 24);
+            rec[8] = (unsigned)g.S.s2.i1 | ((unsigned)g.S.s2.i2 << 8) | ((unsigned)g.S.s3.i1 << 16) | ((unsigned)g.S.s3.i2 << 24);
+            __threadfence_block();  // record before its flag
+            state = kIdle;
+          }
+          __syncwarp();
+          if (finished) st_vol(&ready[idx % kS16RingRecords], idx / kS16RingRecords + 1u);
+          freemask |= fin;
+        }
+      }
+      // ---- convert the pairs fetched at the top of this half-trip into their owners' slots ----
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (sl[k] < 0) continue;  // warp-uniform
+        const int s = sl[k];
+        const u64 p0 = q[k][0].x, p1 = q[k][0].y, p2 = q[k][1].x, p3 = q[k][1].y, p4 = q[k][2].x, p5 = q[k][2].y;
+        const float f0 = lo32(p0), f1 = hi32(p0), f2 = lo32(p1);
+        const float cx = __shfl_sync(0xffffffffu, f0, src0), cy = __shfl_sync(0xffffffffu, f1, src0),
+                    cz = __shfl_sync(0xffffffffu, f2, src0);
+        const u64 cxy = pack2(cx, cy), czx = pack2(cz, cx), cyz = pack2(cy, cz);
+        const u64 e0 = sub2(p0, cxy), e1 = sub2(p1, czx), e2 = sub2(p2, cyz), e3 = sub2(p3, cxy), e4 = sub2(p4, czx),
+                  e5 = sub2(p5, cyz);
+        float m = fmaxf(fabsf(lo32(e0)), fabsf(hi32(e0)));
+        m = fmaxf(m, fmaxf(fabsf(lo32(e1)), fabsf(hi32(e1))));
+        m = fmaxf(m, fmaxf(fabsf(lo32(e2)), fabsf(hi32(e2))));
+        m = fmaxf(m, fmaxf(fabsf(lo32(e3)), fabsf(hi32(e3))));
+        m = fmaxf(m, fmaxf(fabsf(lo32(e4)), fabsf(hi32(e4))));
+        m = fmaxf(m, fmaxf(fabsf(lo32(e5)), fabsf(hi32(e5))));
+        const unsigned mb = act ? __float_as_uint(m) : 0u;  // non-negative floats order like their bit patterns
+        const unsigned r1 = __reduce_max_sync(0xffffffffu, second ? 0u : mb);
+        const unsigned r2 = __reduce_max_sync(0xffffffffu, second ? mb : 0u);
+        const float mm = __uint_as_float(second ? r2 : r1);
+        const bool ok = mm > 8.67361737988e-19f;  // 2^-60
+        const float sc = ok ? __fdividef(kS16Scale, mm) : 0.0f;
+        const u64 g0 = mul2s(e0, sc), g1v = mul2s(e1, sc), g2v = mul2s(e2, sc), g3 = mul2s(e3, sc), g4 = mul2s(e4, sc),
+                  g5 = mul2s(e5, sc);
+        // vertices: 0 = (g0.lo, g0.hi, g1.lo)  1 = (g1.hi, g2.lo, g2.hi)  2 = (g3.lo, g3.hi, g4.lo)  3 = (g4.hi, g5.lo, g5.hi)
+        const __half2 x01 = __floats2half2_rn(lo32(g0), hi32(g1v)), x23 = __floats2half2_rn(lo32(g3), hi32(g4));
+        const __half2 y01 = __floats2half2_rn(hi32(g0), lo32(g2v)), y23 = __floats2half2_rn(hi32(g3), lo32(g5));
+        const __half2 z01 = __floats2half2_rn(lo32(g1v), hi32(g2v)), z23 = __floats2half2_rn(lo32(g4), hi32(g5));
+        unsigned char* dst = wslots + (size_t)s * sbytes;
+        if (act) {
+          *reinterpret_cast<uint2*>(dst + lane_off) =
+              make_uint2(*reinterpret_cast<const unsigned*>(&x01), *reinterpret_cast<const unsigned*>(&x23));
+          *reinterpret_cast<uint2*>(dst + lane_off + 16) =
+              make_uint2(*reinterpret_cast<const unsigned*>(&y01), *reinterpret_cast<const unsigned*>(&y23));
+          *reinterpret_cast<uint2*>(dst + lane_off + 32) =
+              make_uint2(*reinterpret_cast<const unsigned*>(&z01), *reinterpret_cast<const unsigned*>(&z23));
+        }
+        {  // header: c0 and W of this lane's body, stored by the lane that holds the first vertex
+          const float ws = kS16WCentre * sc;
+          const float w0 = ok ? fmaf(ws, fabsf(f0), kS16WConst) : 1e30f, w1 = ok ? fmaf(ws, fabsf(f1), kS16WConst) : 1e30f,
+                      w2 = ok ? fmaf(ws, fabsf(f2), kS16WConst) : 1e30f;
+          if (act && lg == 0) {
+            float2* hd = reinterpret_cast<float2*>(dst + (second ? 24 : 0));
+            hd[0] = make_float2(f0, f1);
+            hd[1] = make_float2(f2, w0);
+            hd[2] = make_float2(w1, w2);
+          }
+        }
+        if (lane == s) {  // the owner: its pair starts at the next scan half-trip
+          pair = tk[k];
+          pi1 = ri1[k];
+          pi2 = ri2[k];
+          state = kFresh;
+        }
+        sl[k] = -1;
+      }
+      __syncwarp();  // the slots' stores are ordered before their owners' loads
+      if (exitmask == 0xffffffffu) break;  // every slot has been told: nothing in flight, nothing running
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      atomicAdd(&ring_ctl[2], 1u);
     }
   } else {
     // ================================================ finisher ===============================================
@@ -547,7 +488,7 @@ gjk_slots16_kernel(const float* __restrict__ coord1, const float* __restrict__ c
       const int c = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);  // records ready in order from `cur`
       if (c == 0) {
         if (ld_vol(&ring_ctl[2]) == (unsigned)(CW / kS16Finishers) && ld_vol(&ring_ctl[0]) == cur) break;
-        __nanosleep(idle_ns / 2u);
+        __nanosleep(100);
         continue;
       }
       __threadfence_block();

@@ -350,19 +350,16 @@ int launch_gjk_slots_ws_cw(int n, int nv1, const T* c1, int nv2, const T* c2, Si
   return finish_launch("gjk slots (warp-specialised) kernel");
 }
 // ---- fp16 pre-scan slot kernel (gjk_slots16.cuh): fp32 batches whose bodies have 8 * NB vertices, NB in 4..8 ---------
-// Takes over from the warp-specialised fp32-slot kernel wherever that one is down to 128 slots per SM (one compute warp
-// per scheduler).  OGJK_GJK_KERNEL=slots16 forces it for every supported shape, =slotsws32 keeps the fp32 slots;
-// OGJK_S16_CFG=<D> (development) picks another converter ring depth for the 64+64-vertex dense instance.
+// Bit-exact and tested, but NOT a default: measured on B200 (profiles/r2_experiments.txt, section D) it runs config 2 in
+// 1.07 ms against 0.77 ms for the fp32-slot kernel -- twice the slots, but the conversion and the exact verification
+// of the candidates cost more issue slots than the cheaper scan saves.  OGJK_GJK_KERNEL=slots16 selects it for every
+// supported shape (=slotsws32 names the fp32-slot kernel explicitly); OGJK_S16_CFG=<K> (development) picks another
+// depth of the fetch ring for the 64+64-vertex dense instance.
 bool slots16_shape(int nv1, int nv2) { return nv1 == nv2 && nv1 % 8 == 0 && nv1 >= 32 && nv1 <= 64; }
 bool use_slots16(int nv1, int nv2, int esize) {
-  if (esize != 4 || !slots16_shape(nv1, nv2)) return false;
-  const int force = forced_kernel();
-  if (force == 5) return true;
-  if (force != 0) return false;
-  int lp = 1;
-  return ws_config(nv1, nv2, &lp, esize) == 4;  // 128 fp32 slots: 40..64 vertices per body
+  return esize == 4 && slots16_shape(nv1, nv2) && forced_kernel() == 5;
 }
-template <int NB, bool IDX, int D>
+template <int NB, bool IDX, int K>
 int launch_gjk_slots16_inst(int n, const float* c1, const float* c2, SimplexT<float>* simp, float* dist, float* nrm,
                             int* queue, int* count, const CollisionPair* pairs) {
   const uint16_t* utab = nullptr;
@@ -371,18 +368,13 @@ int launch_gjk_slots16_inst(int n, const float* c1, const float* c2, SimplexT<fl
   if (int rc = ticket_buffer(&ticket)) return rc;
   constexpr size_t smem = s16_smem_bytes(NB, NB);
   static_assert(smem <= 227u * 1024u, "slots do not fit");
-  auto kern = gjk_slots16_kernel<NB, NB, IDX, D>;
+  auto kern = gjk_slots16_kernel<NB, NB, IDX, K>;
   long long grid = 0;
   if (int rc = persistent_grid(kern, kS16Threads, smem, &grid)) return rc;
   const long long need = ((long long)n + kS16Slots - 1) / kS16Slots;
   if (grid > need) grid = need;
   OGJK_CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned), t_stream));
-  const char* ie = getenv("OGJK_S16_IDLE");  // development: idle back-off of the converter warps in ns
-  const unsigned idle_ns = ie ? (unsigned)atoi(ie) : 200u;
-  const char* ae = getenv("OGJK_S16_AGE");  // development: age (SM cycles) at which a fetched pair is converted
-  const unsigned age = ae ? (unsigned)atoi(ae) : 3000u;
-  kern<<<(unsigned)grid, kS16Threads, smem, t_stream>>>(c1, c2, simp, dist, (unsigned)n, utab, ticket, nrm, queue, count, pairs,
-                                                        idle_ns, age);
+  kern<<<(unsigned)grid, kS16Threads, smem, t_stream>>>(c1, c2, simp, dist, (unsigned)n, utab, ticket, nrm, queue, count, pairs);
   return finish_launch("gjk slots (fp16 pre-scan) kernel");
 }
 template <int NB>
@@ -390,7 +382,7 @@ int launch_gjk_slots16_nb(int n, const float* c1, const float* c2, SimplexT<floa
                           int* queue, int* count, const CollisionPair* pairs) {
   if (pairs) return launch_gjk_slots16_inst<NB, true, 4>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
   if constexpr (NB == 8) {
-    const char* e = getenv("OGJK_S16_CFG");  // development: depth of the converters' register ring
+    const char* e = getenv("OGJK_S16_CFG");  // development: pairs a warp keeps in flight
     const int cfg = e ? atoi(e) : 0;
     if (cfg == 2) return launch_gjk_slots16_inst<NB, false, 2>(n, c1, c2, simp, dist, nrm, queue, count, pairs);
     if (cfg == 3) return launch_gjk_slots16_inst<NB, false, 3>(n, c1, c2, simp, dist, nrm, queue, count, pairs);

@@ -43,13 +43,9 @@ if __name__ == '__main__':
     nv = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     spread = float(sys.argv[2]) if len(sys.argv) > 2 else 10.0
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 20
-    variants = [("fp32 slots (ws)", {"OGJK_GJK_KERNEL": "slotsws32"}), ("fp16 slots D4", {"OGJK_GJK_KERNEL": "slots16"})]
+    variants = [("fp32 slots (ws)", {"OGJK_GJK_KERNEL": "slotsws32"}), ("fp16 slots K4", {"OGJK_GJK_KERNEL": "slots16"})]
     if nv == 64:
-        variants += [(f"fp16 slots D{c}", {"OGJK_GJK_KERNEL": "slots16", "OGJK_S16_CFG": str(c)}) for c in (2, 3, 5)]
-    if nv == 64:
-        variants += [(f"fp16 D4 age {a}", {"OGJK_GJK_KERNEL": "slots16", "OGJK_S16_AGE": str(a)}) for a in (1000, 2000, 4000, 6000)]
-        variants += [(f"fp16 D5 age {a}", {"OGJK_GJK_KERNEL": "slots16", "OGJK_S16_CFG": "5", "OGJK_S16_AGE": str(a)}) for a in (2000, 4000)]
-        variants += [(f"fp16 D4 idle {ns}", {"OGJK_GJK_KERNEL": "slots16", "OGJK_S16_IDLE": str(ns)}) for ns in (50, 800)]
+        variants += [(f"fp16 slots K{c}", {"OGJK_GJK_KERNEL": "slots16", "OGJK_S16_CFG": str(c)}) for c in (2, 3, 5)]
     if nv == 32:
         variants.insert(0, ("fp32 slots (self)", {"OGJK_GJK_KERNEL": "slots"}))
     run(n, nv, spread, variants)

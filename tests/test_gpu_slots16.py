@@ -69,7 +69,7 @@ def test_slots16_matches_oracle(pkg, oracle_mod, force_kernel, nv, spread):
 
 @pytest.mark.parametrize("cfg", [2, 3, 5])
 def test_slots16_converter_configurations(pkg, oracle_mod, force_kernel, cfg):
-    """the other converter ring depths of the 64+64-vertex kernel"""
+    """the other fetch-ring depths of the 64+64-vertex kernel"""
     n = 60000
     a, b = pkg.workloads.random_pairs(n, 64, 10.0, seed=5, dtype=np.float32)
     force_kernel("slots16", cfg)
