@@ -454,14 +454,18 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         centroid.z = add_rn(centroid.z, mul_rn(sub_rn(w.z, centroid.z), inv_n));
       }
 
-      // faces that see the new vertex die; their directed edges go to the scratch list in (slot, corner) order
-      int nvis = 0;
+      // faces that see the new vertex die; their directed edges go to the scratch list in (slot, corner) order.  An edge
+      // a -> b is stored as  min | max << 8 | (a > b) << 15 : the low 15 bits are the UNDIRECTED edge, which is what the
+      // horizon test compares.  The same pass ranks the free slots below `hi` (free before, or dying now) for the new
+      // faces; slots at or above `hi` are all free and need no table.
+      int nvis = 0, nfree_lo = 0;
       for (int j = 0; j < njw; ++j) {
         const int f = g.lane + G * j;
         uint32_t word = 0;
-        bool sees = false;
+        bool sees = false, in_range = false;
         if (act && j < nj) {
           word = W.fv[f];
+          in_range = f < hi;
           if (word >> 24) {
             const int a = word & 0xff;
             const V3<T> diff = vsub(w, work_vertex(W, a));
@@ -469,72 +473,79 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
           }
         }
         const unsigned vm = gw.ballot(sees);
+        const bool free_now = in_range && ((word >> 24) == 0 || sees);
+        const unsigned fm = gw.ballot(free_now);
         if (sees) {
           const int rank = nvis + __popc(vm & g.below());
           const uint32_t a = word & 0xff, b = (word >> 8) & 0xff, c = (word >> 16) & 0xff;
           if (3 * rank + 2 < WT::kEdges) {
-            W.edge[3 * rank + 0] = (uint16_t)((a << 8) | b);
-            W.edge[3 * rank + 1] = (uint16_t)((b << 8) | c);
-            W.edge[3 * rank + 2] = (uint16_t)((c << 8) | a);
+            W.edge[3 * rank + 0] = (uint16_t)(a < b ? (a | (b << 8)) : (b | (a << 8) | 0x8000u));
+            W.edge[3 * rank + 1] = (uint16_t)(b < c ? (b | (c << 8)) : (c | (b << 8) | 0x8000u));
+            W.edge[3 * rank + 2] = (uint16_t)(c < a ? (c | (a << 8)) : (a | (c << 8) | 0x8000u));
           }
           W.fv[f] = word & 0x00ffffffu;  // retire
         }
+        if (free_now) {
+          const int r = nfree_lo + __popc(fm & g.below());
+          if (!WT::kSmall || r < WT::kEdges) W.rank2slot[r] = (uint8_t)f;
+        }
         nvis += __popc(vm);
+        nfree_lo += __popc(fm);
       }
-      __syncwarp();
       if (WT::kSmall && act && 3 * nvis > WT::kEdges) {  // more dying faces than the edge list holds
         ovf = true;
         act = false;
         nvis = 0;
       }
       const int nedge = 3 * nvis;  // 0 for inactive groups
+      if (act && g.lane < 3 && (nedge & 3) && nedge + g.lane < ((nedge + 3) & ~3))  // pad to a whole 64-bit word
+        W.edge[nedge + g.lane] = 0xffffu;
       const int nedgew = __reduce_max_sync(0xffffffffu, nedge);
-
-      // r-th lowest free slot for r < nedge: slots at or above `hi` are all free, so [0, hi + nedge) always holds
-      // enough -- unless the 128 slots run out, in which case the remaining edges are dropped (EPA.c:775)
-      int nfree = 0;
-      {
-        const int limit = !act ? 0 : (hi + nedge < WT::kFaces ? hi + nedge : WT::kFaces);
-        const int limitw = __reduce_max_sync(0xffffffffu, limit);
-        for (int j = 0; G * j < limitw; ++j) {
-          const int f = g.lane + G * j;
-          const bool is_free = f < limit && (W.fv[f] >> 24) == 0;
-          const unsigned fm = gw.ballot(is_free);
-          const int r = nfree + __popc(fm & g.below());
-          if (is_free && (!WT::kSmall || r < WT::kEdges)) W.rank2slot[r] = (uint8_t)f;
-          nfree += __popc(fm);
-        }
-      }
+      // r-th lowest free slot for r < nfree: the table below `hi`, then hi, hi + 1, ... -- unless the slots run out, in
+      // which case the remaining edges are dropped (EPA.c:775)
+      const int limit = !act ? 0 : (hi + nedge < WT::kFaces ? hi + nedge : WT::kFaces);
+      const int nfree = !act ? 0 : nfree_lo + (limit - hi);
+      auto free_slot = [&](int r) { return r < nfree_lo ? (int)W.rank2slot[r] : hi + (r - nfree_lo); };
       __syncwarp();
 
-      // horizon = edges that occur exactly once (EPA.c:745-759); each gets the next lowest free slot, in edge
-      // order (EPA.c:761-775)
-      int base_rank = 0;
-      bool any_degenerate = false;
+      // horizon = edges that occur exactly once, in either direction (EPA.c:745-759); each gets the next lowest free
+      // slot, in edge order (EPA.c:761-775).  Four list entries per 64-bit load; no collective inside the inner loop, so
+      // its trip count is the group's own.
       // (Measured and dropped: letting the whole warp test one group's edge list after the other with match.any on the
       // undirected key instead of this all-pairs loop -- config 3 went from 6.29 to 7.27 ms per Mi pairs,
       // profiles/r2d_ab_epa.txt: eight MATCH + VOTE + SHFL rounds per expansion cost more than the loop they replace.)
+      int base_rank = 0;
+      bool any_degenerate = false;
+      const uint2* edge4 = reinterpret_cast<const uint2*>(W.edge);
       for (int e0 = 0; e0 < nedgew; e0 += G) {
         const int e = e0 + g.lane;
         bool keep = e < nedge;
-        uint32_t key = 0, rev = 0;
+        uint32_t key = 0xffffu;
         if (keep) {
           key = W.edge[e];
-          rev = ((key & 0xff) << 8) | (key >> 8);
-        }
-        for (int x = 0; x < nedgew; ++x) {
-          if (x < nedge) {
-            const uint32_t other = W.edge[x];
-            if (x != e && (other == key || other == rev)) keep = false;
+          const uint32_t und2 = (key & 0x7fffu) * 0x10001u;
+          // per 16-bit half: (entry & 0x7fff) ^ key is 0 on a match; adding 0x7fff sets bit 15 of every NON-zero half
+          // (no carry leaves a half: 0x7fff + 0x7fff < 0x10000); the halves that stay clear are the matches
+          uint32_t miss = 0;
+          int halves = 0;
+          for (int x = 0; x < nedge; x += 4) {
+            const uint2 four = edge4[x >> 2];
+            miss += (((four.x & 0x7fff7fffu) ^ und2) + 0x7fff7fffu) >> 15 & 0x00010001u;
+            miss += (((four.y & 0x7fff7fffu) ^ und2) + 0x7fff7fffu) >> 15 & 0x00010001u;
+            halves += 4;
           }
+          const int cnt = halves - (int)((miss & 0xffffu) + (miss >> 16));
+          keep = cnt == 1;  // only itself
         }
         const unsigned keepm = gw.ballot(keep);
         if (keep) {
           const int q2 = base_rank + __popc(keepm & g.below());
           if (q2 < nfree) {
-            const int slot = W.rank2slot[q2];
+            const int slot = free_slot(q2);
+            const int lo = (int)(key & 0xffu), hi8 = (int)((key >> 8) & 0x7fu);
+            const bool rev = (key & 0x8000u) != 0u;
             bool degenerate = false;
-            const uint32_t word = make_face(W, slot, (int)(key >> 8), (int)(key & 0xff), newv, centroid, degenerate);
+            const uint32_t word = make_face(W, slot, rev ? hi8 : lo, rev ? lo : hi8, newv, centroid, degenerate);
             W.fv[slot] = word;
             if (degenerate) any_degenerate = true;
           }
@@ -554,7 +565,7 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
       if (act) {
         const int used = base_rank < nfree ? base_rank : nfree;
         if (used > 0) {
-          const int top = (int)W.rank2slot[used - 1] + 1;  // ranks ascend with slots
+          const int top = free_slot(used - 1) + 1;  // ranks ascend with slots
           hi = top > hi ? top : hi;
         }
       }

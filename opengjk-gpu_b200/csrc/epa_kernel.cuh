@@ -224,7 +224,7 @@ OGJK_D uint32_t make_face(WT& W, int f, int a, int b, int c, const V3<typename W
   T d;
   if (len2 > mul_rn(eps, eps)) {
     const T len = sqrt_rn(len2);
-    nrm = mk<T>(div_rn(nrm.x, len), div_rn(nrm.y, len), div_rn(nrm.z, len));
+    div3_rn(nrm.x, nrm.y, nrm.z, len);  // three correctly rounded quotients, one reciprocal
     d = dot(nrm, va);
     if (d < T(0)) {
       nrm = vneg(nrm);

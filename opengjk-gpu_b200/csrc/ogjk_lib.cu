@@ -527,12 +527,13 @@ int launch_epa_group(const Source& src, int n, SimplexT<T>* d_simplices, T* d_di
   return launch_epa_warp_queue<T, Source>(src, n, d_simplices, d_distances, d_normals, q.overflow, q.counters + 2, sms);
 }
 
-// Persistent EPA over a device-side queue of colliding pairs.  Default (measured on B200, profiles/r2b_ab_epa.txt):
+// Persistent EPA over a device-side queue of colliding pairs.  Default (measured on B200, profiles/r2q_ab_epa.txt):
 // bodies of up to 32 vertices take the sub-warp group kernel with the small work area, G = 4 lanes per pair, followed
-// by the overflow pass -- config 3: 6.29 ms against 7.66 ms per Mi pairs for one warp per pair, config 5: 11.4
-// against 14.1 ms per 4 M pairs; larger bodies (the support scan grows, the bookkeeping does not) take one warp per
-// pair -- 64 vertices: 3.43 ms against 3.56 (G = 8) and 4.53 (G = 4) per 512 Ki deep pairs.  Development overrides:
-// OGJK_EPA_KERNEL=warp|group (group = full-size work area, 8 lanes)|small4|small8.
+// by the overflow pass -- config 3: 5.88 ms against 7.64 ms per Mi pairs for one warp per pair, config 5: 10.6
+// against 14.1 ms per 4 M pairs, 16-vertex bodies 4.34 against 6.43; larger bodies (the support scan grows, the
+// bookkeeping does not) take one warp per pair -- config 2 (64 vertices, shallow contacts): 0.29 ms against 0.33 (G = 8)
+// and 0.48 (G = 4); only deep 64-vertex contacts favour G = 8 (3.04 against 3.42 ms per 512 Ki pairs).  Development
+// overrides: OGJK_EPA_KERNEL=warp|group (group = full-size work area, 8 lanes)|small4|small8.
 template <typename T, typename Source>
 int launch_epa_queue(const Source& src, int n, int nv_hint, SimplexT<T>* d_simplices, T* d_distances, T* d_normals,
                      const EpaQueue& q) {
