@@ -246,6 +246,79 @@ OGJK_D void support_slots_both(const float* b1, const float* b2, int nv, const V
   recover_support(b2, c2, bg2, best2, D2, v, sup2, idx2);
 }
 
+// ---- SoA-4 packed bodies (indexed pools re-packed on the device: x0..x3 | y0..y3 | z0..z3 per block of four vertices) --
+// With the coordinates transposed the two additions of a dot product can be packed as well: FFMA2(p, 1, q) rounds p + q
+// once, exactly like the reference's unfused add (`one` is an opaque 1.0f so that ptxas can neither fold the multiply by
+// one nor contract it with the preceding FMUL2).  Ten issue slots per four vertices instead of fourteen.
+OGJK_D u64 mul2b(u64 a, float s) {  // both halves times s
+  u64 ss, r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(ss));
+  return r;
+}
+OGJK_D u64 add2_via_fma(u64 p, u64 one2, u64 q) {  // (p.lo + q.lo, p.hi + q.hi), each rounded once
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(p), "l"(one2), "l"(q));
+  return r;
+}
+OGJK_D void dots4_pk(const Block4& k, const V3<float>& d, u64 one2, float (&dd)[4]) {
+  const u64 s01 = add2_via_fma(mul2b(k.c.x, d.z), one2, add2_via_fma(mul2b(k.b.x, d.y), one2, mul2b(k.a.x, d.x)));
+  const u64 s23 = add2_via_fma(mul2b(k.c.y, d.z), one2, add2_via_fma(mul2b(k.b.y, d.y), one2, mul2b(k.a.y, d.x)));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(dd[0]), "=f"(dd[1]) : "l"(s01));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(dd[2]), "=f"(dd[3]) : "l"(s23));
+}
+OGJK_D V3<float> packed_vertex(const float* body, int i) {
+  const float* b = body + 12 * (i >> 2) + (i & 3);
+  return mk<float>(b[0], b[4], b[8]);
+}
+OGJK_D void recover_support_pk(const float* body, const ulonglong2* chunk, int bg, float best, const V3<float>& d, u64 one2,
+                               V3<float>& sup, int& sup_idx) {
+  if (best > dot(sup, d)) {
+    float dd[4];
+    dots4_pk(load_block(chunk, bg), d, one2, dd);
+    int k = 3;
+    if (dd[2] == best) k = 2;
+    if (dd[1] == best) k = 1;
+    if (dd[0] == best) k = 0;
+    const int idx = 4 * bg + k;
+    sup = packed_vertex(body, idx);
+    sup_idx = idx;
+  }
+}
+// both bodies of a pair in one loop, as support_slots_both
+OGJK_D void support_slots_both_pk(const float* b1, const float* b2, int nv, const V3<float>& v, unsigned zero,
+                                  V3<float>& sup1, int& idx1, V3<float>& sup2, int& idx2) {
+  const ulonglong2* c1 = reinterpret_cast<const ulonglong2*>(b1);
+  const ulonglong2* c2 = reinterpret_cast<const ulonglong2*>(b2);
+  const V3<float> nvv = vneg(v);
+  const float one = __uint_as_float(0x3f800000u ^ zero);
+  const u64 one2 = pack2(one, one);
+  float best1 = -INFINITY, best2 = -INFINITY;
+  int bg1 = 0, bg2 = 0;
+  const int groups = nv >> 2;
+  Block4 a0 = load_block(c1, 0), e0 = load_block(c2, 0);
+#pragma unroll 2
+  for (int t = 0; t < groups; ++t) {
+    const Block4 na0 = load_block(c1, t + 1), ne0 = load_block(c2, t + 1);  // look-ahead; past the end it is discarded
+    float da[4], dc[4];
+    dots4_pk(a0, nvv, one2, da);
+    dots4_pk(e0, v, one2, dc);
+    const float ma = max4(da), mc = max4(dc);
+    if (ma > best1) {  // strict: the earliest block holding the maximum wins
+      best1 = ma;
+      bg1 = t;
+    }
+    if (mc > best2) {
+      best2 = mc;
+      bg2 = t;
+    }
+    a0 = na0;
+    e0 = ne0;
+  }
+  recover_support_pk(b1, c1, bg1, best1, nvv, one2, sup1, idx1);
+  recover_support_pk(b2, c2, bg2, best2, v, one2, sup2, idx2);
+}
+
 // ---- per-warp ticket feed ------------------------------------------------------------------------------------------
 // Pair indices are handed out through one global counter, 32 at a time per warp.  A warp holds the chunk it is
 // consuming and prepares the NEXT one in the background, in three steps spread over successive calls so that neither
@@ -391,6 +464,16 @@ struct SlotFetch {
   }
 };
 
+template <typename T>
+struct SlotFetchPacked {  // SoA-4 packed slots (fp32 only)
+  const T* b1;
+  const T* b2;
+  OGJK_D V3<T> operator()(int body, int i) const {
+    const T* c = (body ? b2 : b1) + 12 * (i >> 2) + (i & 3);
+    return mk<T>(c[0], c[4], c[8]);
+  }
+};
+
 constexpr int kSlotThreads = 128;
 constexpr uint32_t kSlotTableBytes = (kUnifiedSize * 2u + 15u) & ~15u;
 constexpr uint32_t kSlotFixedBytes = kSlotThreads * 8u + kSlotTableBytes;  // mbarriers + table
@@ -403,9 +486,24 @@ __host__ __device__ inline uint32_t slot_bytes(int nv1, int nv2, int esize = 4) 
   return units * 16u;
 }
 
+// pool [count][nv][3] -> [count][nv / 4][3][4]; one thread per vertex
+__global__ void pack_pool_kernel(const float* __restrict__ in, float* __restrict__ out, int nv, long long total_vertices) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= total_vertices) return;
+  const long long body = v / nv;
+  const int i = (int)(v - body * nv);
+  const float* src = in + 3 * v;
+  float* dst = out + body * nv * 3 + 12 * (i >> 2) + (i & 3);
+  dst[0] = src[0];
+  dst[4] = src[1];
+  dst[8] = src[2];
+}
+
 // EQ: both bodies have the same vertex count (selects the interleaved two-body scan; the other scan is not even
 // instantiated then, which keeps the loop body small for the instruction cache)
-template <typename T, bool EQ>
+// PK: the bodies are SoA-4 packed (x0..x3 | y0..y3 | z0..z3 per four vertices; fp32, equal vertex counts): the pool of an
+// indexed batch re-packed on the device by pack_pool_kernel
+template <typename T, bool EQ, bool PK = false>
 __global__ void __launch_bounds__(kSlotThreads)
 gjk_slots_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, int nv1, int nv2,
                  SimplexT<T>* __restrict__ simplices, T* __restrict__ distances, unsigned n,
@@ -461,21 +559,29 @@ gjk_slots_kernel(const T* __restrict__ coord1, const T* __restrict__ coord2, int
 
     if (state == kLoading && mbar_test_wait(bar, parity)) {
       parity ^= 1u;
-      gjk_init(g, mk<T>(s1[0], s1[1], s1[2]), mk<T>(s2[0], s2[1], s2[2]));
+      if (PK) gjk_init(g, mk<T>(s1[0], s1[4], s1[8]), mk<T>(s2[0], s2[4], s2[8]));
+      else gjk_init(g, mk<T>(s1[0], s1[1], s1[2]), mk<T>(s2[0], s2[1], s2[2]));
       state = kRunning;
     }
     if (state == kRunning) {
       ++g.k;
-      if (EQ) {
+      if constexpr (PK) {
+        support_slots_both_pk(s1, s2, nv1, g.v, zero, g.sup1, g.idx1, g.sup2, g.idx2);
+      } else if (EQ) {
         support_slots_both(s1, s2, nv1, g.v, zero, g.sup1, g.idx1, g.sup2, g.idx2);
       } else {
         support_slot(s1, nv1, vneg(g.v), zero, g.sup1, g.idx1);
         support_slot(s2, nv2, g.v, zero, g.sup2, g.idx2);
       }
       if (gjk_advance_u(g, utab)) {
-        SlotFetch<T> fetch{s1, s2};
         V3<T> w1, w2;
-        gjk_witnesses(fetch, g.S, w1, w2);
+        if constexpr (PK) {
+          SlotFetchPacked<T> fetch{s1, s2};
+          gjk_witnesses(fetch, g.S, w1, w2);
+        } else {
+          SlotFetch<T> fetch{s1, s2};
+          gjk_witnesses(fetch, g.S, w1, w2);
+        }
         store_result(simplices + pair, distances + pair, g, w1, w2);
         state = kNeedWork;
       }

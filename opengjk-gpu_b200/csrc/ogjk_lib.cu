@@ -228,7 +228,7 @@ struct StreamScratch {
   int dev = -1;
   cudaStream_t stream = nullptr;
   unsigned* ticket = nullptr;
-  Scratch epa, bp, cr, flag;
+  Scratch epa, bp, cr, flag, pack;
 };
 thread_local std::vector<StreamScratch> t_sscratch;
 int stream_scratch(StreamScratch** out) {
@@ -276,23 +276,51 @@ int forced_kernel() {
          !strcmp(e, "slotsws") ? 4 : !strcmp(e, "slots16") ? 5 : !strcmp(e, "slotsws32") ? 6 : 0;
 }
 
+// Indexed batches over one fp32 pool can have the pool re-packed on the device into SoA-4 blocks (x0..x3 | y0..y3 |
+// z0..z3) in front of the self-service slot kernel -- one pass over the pool, which an indexed batch reads hundreds of
+// times -- so that the scan runs with packed multiplies AND packed adds (gjk_slots.cuh, dots4_pk: 10 instead of 14
+// issue slots per four vertices).  Bit-exact, measured, and NOT the default: config 5 (20 000 x 32 vertices, 3.96 M
+// pairs) 1.846 ms packed against 1.803 ms plain (profiles/r2r_ab_pool_pack.txt) -- the kernel waits on dependent
+// results, not on issue slots.  OGJK_POOL_PACK=1 turns it on.
+bool use_packed_pool(long long, int pool_count) {
+  const char* e = getenv("OGJK_POOL_PACK");
+  return e && atoi(e) != 0 && pool_count > 0;
+}
+
 template <typename T>
 int launch_gjk_slots(int n, int nv1, const T* c1, int nv2, const T* c2, SimplexT<T>* simp, T* dist,
-                     const CollisionPair* pairs = nullptr) {
+                     const CollisionPair* pairs = nullptr, int pool_count = 0) {
   const uint16_t* utab = nullptr;
   if (int rc = device_unified_table(&utab)) return rc;
   unsigned* ticket = nullptr;
   if (int rc = ticket_buffer(&ticket)) return rc;
   const size_t smem = (size_t)kSlotFixedBytes + kSlotPadBytes + (size_t)kSlotThreads * slot_bytes(nv1, nv2, (int)sizeof(T));
   // the interleaved scan needs ~40 more registers: only where shared memory, not registers, bounds occupancy
-  auto kern = (sizeof(T) == 4 && nv1 == nv2 && nv1 >= 32) ? gjk_slots_kernel<T, true> : gjk_slots_kernel<T, false>;
+  const bool eq = sizeof(T) == 4 && nv1 == nv2 && nv1 >= 32;
+  auto kern = eq ? gjk_slots_kernel<T, true> : gjk_slots_kernel<T, false>;
+  bool packed = false;
+  if constexpr (sizeof(T) == 4) {
+    if (eq && pairs && c1 == c2 && pool_count > 0 && use_packed_pool(n, pool_count)) {
+      StreamScratch* ss = nullptr;
+      if (int rc = stream_scratch(&ss)) return rc;
+      int* buf = nullptr;
+      const long long verts = (long long)pool_count * nv1;
+      if (int rc = scratch_grow(ss->pack, (size_t)verts * 3, &buf)) return rc;
+      pack_pool_kernel<<<(unsigned)((verts + 255) / 256), 256, 0, t_stream>>>(c1, reinterpret_cast<float*>(buf), nv1, verts);
+      ++t_launches;
+      OGJK_CK(cudaGetLastError());
+      c1 = c2 = reinterpret_cast<const T*>(buf);
+      kern = gjk_slots_kernel<T, true, true>;
+      packed = true;
+    }
+  }
   long long grid = 0;
   if (int rc = persistent_grid(kern, kSlotThreads, smem, &grid)) return rc;
   const long long need = ((long long)n + kSlotThreads - 1) / kSlotThreads;
   if (grid > need) grid = need;
   OGJK_CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned), t_stream));
   kern<<<(unsigned)grid, kSlotThreads, smem, t_stream>>>(c1, c2, nv1, nv2, simp, dist, (unsigned)n, utab, ticket, 0u, pairs);
-  return finish_launch("gjk slots kernel");
+  return finish_launch(packed ? "gjk slots kernel (SoA-4 packed pool)" : "gjk slots kernel");
 }
 
 // tickets per atomic of the ws loader on dense batches (>= 32); development override OGJK_WS_CHUNK
@@ -706,7 +734,7 @@ int launch_indexed_uniform(int n, const PoolInfo& pool, const CollisionPair* d_p
   const bool epa = (stages & kEpaStage) != 0;
   if (!epa) {
     return ws ? launch_gjk_slots_ws<T>(n, nv, base, nv, base, simp, dist, nullptr, nullptr, nullptr, d_pairs)
-              : launch_gjk_slots<T>(n, nv, base, nv, base, simp, dist, d_pairs);
+              : launch_gjk_slots<T>(n, nv, base, nv, base, simp, dist, d_pairs, pool.count);
   }
   if (!nrm) return fail_msg("contact_normals must not be NULL on the device path");
   IndexedSource<T> src{d_desc, d_pairs};
@@ -730,7 +758,7 @@ int launch_indexed_uniform(int n, const PoolInfo& pool, const CollisionPair* d_p
     if (!rc) rc = stage_mark(2);
     return rc;
   }
-  rc = launch_gjk_slots<T>(n, nv, base, nv, base, simp, dist, d_pairs);
+  rc = launch_gjk_slots<T>(n, nv, base, nv, base, simp, dist, d_pairs, pool.count);
   t_sync = sync_saved;
   if (!rc) rc = stage_mark(1);
   if (!rc) rc = launch_epa<T>(src, n, nv, simp, dist, nrm);
@@ -1512,7 +1540,7 @@ int ogjk_release_cached_buffers(void) {
     OGJK_CK(cudaSetDevice(x.dev));
     cudaFree(x.ticket);
     x.ticket = nullptr;
-    for (Scratch* sc : {&x.epa, &x.bp, &x.cr, &x.flag}) {
+    for (Scratch* sc : {&x.epa, &x.bp, &x.cr, &x.flag, &x.pack}) {
       cudaFree(sc->ptr);
       sc->ptr = nullptr;
       sc->ints = 0;

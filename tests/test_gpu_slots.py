@@ -178,3 +178,28 @@ def test_indexed_uniform_pool_takes_slot_kernels(pkg, oracle_mod, force_kernel, 
         assert np.array_equal(d5, ed) and live_simplex_equal(s5, es)
     finally:
         eng.free_indexed_device(dp, dc, dpairs, dsimp, ddist, dnrm)
+
+
+@pytest.mark.parametrize("nverts", [32, 64])
+def test_indexed_pool_soa4_packed(pkg, oracle_mod, force_kernel, nverts):
+    """the SoA-4 re-packed pool (packed multiplies and packed adds in the scan) against the oracle, and against the
+    same batch through the unpacked pool"""
+    npoly = 1500
+    pool, pairs = pkg.workloads.broadphase_pool(npoly, nverts, 45000, seed=23)
+    off = np.arange(npoly + 1) * nverts
+    gs, gd, _ = oracle_mod.Oracle("port", np.float32).gjk_epa_indexed(pool.reshape(-1, 3), pairs, off, do_epa=False, nthreads=8)
+    eng = pkg.Engine(np.float32)
+    desc, _keep = pkg.make_polytopes(pool)
+    force_kernel("slots")
+    saved = os.environ.get("OGJK_POOL_PACK")
+    try:
+        for pack in ("1", "0"):
+            os.environ["OGJK_POOL_PACK"] = pack
+            s, d = eng.compute_minimum_distance_indexed(desc, pairs)
+            assert ("SoA-4" in eng.last_kernel()) == (pack == "1")
+            assert np.array_equal(d, gd) and live_simplex_equal(s, gs)
+    finally:
+        if saved is None:
+            os.environ.pop("OGJK_POOL_PACK", None)
+        else:
+            os.environ["OGJK_POOL_PACK"] = saved
