@@ -5,6 +5,9 @@
  * contact_normals = nullptr) (reference README.md:38-47) that the reference documents but never defines.
  * As in the reference (examples/gpu/example.cu:42-45, 75-78, 110-112), timer() brackets only the *_device launches --
  * not allocation, upload, download or free -- for all three entry points.
+ * Multi-GPU: when more than one device has been selected (ogjk_set_devices() or OGJK_DEVICES in the environment) the
+ * three entry points hand the host arrays to the library's host-pointer calls, which slice the pair range over the
+ * devices; timer() then brackets the whole fanned-out call (the kernels of different devices have no common clock).
  */
 #ifndef EXAMPLE_H
 #define EXAMPLE_H
@@ -23,6 +26,12 @@ inline GJK::Common::PerformanceTimer& timer() {
 inline void computeDistances(const int n, const gkPolytope* bd1, const gkPolytope* bd2, gkSimplex* simplices,
                              gkFloat* distances) {
   if (n <= 0) return;
+  if (ogjk_selected_device_count() > 1) {
+    timer().startGpuTimer();
+    compute_minimum_distance(n, bd1, bd2, simplices, distances);
+    timer().endGpuTimer();
+    return;
+  }
   gkPolytope *d_bd1 = nullptr, *d_bd2 = nullptr;
   gkFloat *d_coord1 = nullptr, *d_coord2 = nullptr, *d_distances = nullptr;
   gkSimplex* d_simplices = nullptr;
@@ -45,6 +54,12 @@ inline gkFloat* alloc_normals(const int n) {
 inline void computeEPA(const int n, const gkPolytope* bd1, const gkPolytope* bd2, gkSimplex* simplices,
                        gkFloat* distances, gkFloat* contact_normals) {
   if (n <= 0) return;
+  if (ogjk_selected_device_count() > 1) {
+    timer().startGpuTimer();
+    computeCollisionInformation(n, bd1, bd2, simplices, distances, contact_normals);
+    timer().endGpuTimer();
+    return;
+  }
   gkPolytope *d_bd1 = nullptr, *d_bd2 = nullptr;
   gkFloat *d_coord1 = nullptr, *d_coord2 = nullptr, *d_distances = nullptr;
   gkSimplex* d_simplices = nullptr;
@@ -64,6 +79,12 @@ inline void computeEPA(const int n, const gkPolytope* bd1, const gkPolytope* bd2
 inline void computeGJKAndEPA(const int n, const gkPolytope* bd1, const gkPolytope* bd2, gkSimplex* simplices,
                              gkFloat* distances, gkFloat* contact_normals) {
   if (n <= 0) return;
+  if (ogjk_selected_device_count() > 1) {
+    timer().startGpuTimer();
+    compute_gjk_epa(n, bd1, bd2, simplices, distances, contact_normals);
+    timer().endGpuTimer();
+    return;
+  }
   gkPolytope *d_bd1 = nullptr, *d_bd2 = nullptr;
   gkFloat *d_coord1 = nullptr, *d_coord2 = nullptr, *d_distances = nullptr;
   gkSimplex* d_simplices = nullptr;

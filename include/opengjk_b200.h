@@ -58,6 +58,8 @@ int ogjk_set_sync(int enabled);
  * selection can be made without touching the caller's code through the environment: OGJK_DEVICES=all | <count> |
  * <i,j,...>.  Process-wide.  The *_device entry points always use the calling thread's current device. */
 int ogjk_set_devices(int count, const int* devices);
+/* Number of devices the host-pointer entry points currently fan out over (0 or 1: single-device behaviour). */
+int ogjk_selected_device_count(void);
 /* Frees the device buffers the calling thread has cached (the host-pointer path keeps its staging buffers between
  * calls instead of cudaMalloc/cudaFree per call as the reference does, openGJK.cu:2889-2954, 3034-3048; scratch of the
  * EPA queue / broad phase / contact response).  No call of this thread may be in flight. */

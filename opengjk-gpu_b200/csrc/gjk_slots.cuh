@@ -185,6 +185,36 @@ OGJK_D void recover_support(const float* body, const ulonglong2* chunk, int bg, 
     sup_idx = idx;
   }
 }
+// (max, block) update of both bodies for blocks g and g + 1
+OGJK_D void scan_two_blocks(const Block4& a0, const Block4& a1, const Block4& e0, const Block4& e1, const DirPack& D1,
+                            const DirPack& D2, int g, float& best1, int& bg1, float& best2, int& bg2) {
+  float da[4], db[4], dc[4], de[4];
+  dots4(a0, D1, da);
+  dots4(e0, D2, dc);
+  dots4(a1, D1, db);
+  dots4(e1, D2, de);
+  const float ma = max4(da), mc = max4(dc), mb = max4(db), me = max4(de);
+  if (ma > best1) {
+    best1 = ma;
+    bg1 = g;
+  }
+  if (mc > best2) {
+    best2 = mc;
+    bg2 = g;
+  }
+  if (mb > best1) {
+    best1 = mb;
+    bg1 = g + 1;
+  }
+  if (me > best2) {
+    best2 = me;
+    bg2 = g + 1;
+  }
+}
+// Two register sets: while set A (blocks 2t, 2t+1 of both bodies) is evaluated the loads of set B (blocks 2t+2, 2t+3)
+// are in flight and vice versa.  (With ONE set and `current = next` at the end of the trip the compiler lets `next` share
+// the registers of `current`, so a load can only issue after the last use of the block it replaces: nine of the twelve
+// loads of a trip ended up in its last 22 instructions and the first multiply of the next trip waited for them.)
 OGJK_D void support_slots_both(const float* b1, const float* b2, int nv, const V3<float>& v, unsigned zero,
                                V3<float>& sup1, int& idx1, V3<float>& sup2, int& idx2) {
   const ulonglong2* c1 = reinterpret_cast<const ulonglong2*>(b1);
@@ -197,38 +227,25 @@ OGJK_D void support_slots_both(const float* b1, const float* b2, int nv, const V
   const int pairs = groups >> 1;
   Block4 a0 = load_block(c1, 0), a1 = load_block(c1, 1);
   Block4 e0 = load_block(c2, 0), e1 = load_block(c2, 1);
+  int t = 0;
 #pragma unroll 1
-  for (int t = 0; t < pairs; ++t) {
-    const Block4 na0 = load_block(c1, 2 * t + 2), na1 = load_block(c1, 2 * t + 3);
-    const Block4 ne0 = load_block(c2, 2 * t + 2), ne1 = load_block(c2, 2 * t + 3);
-    float da[4], db[4], dc[4], de[4];
-    dots4(a0, D1, da);
-    dots4(e0, D2, dc);
-    dots4(a1, D1, db);
-    dots4(e1, D2, de);
-    const float ma = max4(da), mc = max4(dc), mb = max4(db), me = max4(de);
-    if (ma > best1) {
-      best1 = ma;
-      bg1 = 2 * t;
-    }
-    if (mc > best2) {
-      best2 = mc;
-      bg2 = 2 * t;
-    }
-    if (mb > best1) {
-      best1 = mb;
-      bg1 = 2 * t + 1;
-    }
-    if (me > best2) {
-      best2 = me;
-      bg2 = 2 * t + 1;
-    }
-    a0 = na0;
-    a1 = na1;
-    e0 = ne0;
-    e1 = ne1;
+  for (; t + 2 <= pairs; t += 2) {
+    const Block4 p0 = load_block(c1, 2 * t + 2), p1 = load_block(c1, 2 * t + 3);
+    const Block4 r0 = load_block(c2, 2 * t + 2), r1 = load_block(c2, 2 * t + 3);
+    scan_two_blocks(a0, a1, e0, e1, D1, D2, 2 * t, best1, bg1, best2, bg2);
+    a0 = load_block(c1, 2 * t + 4);
+    a1 = load_block(c1, 2 * t + 5);
+    e0 = load_block(c2, 2 * t + 4);
+    e1 = load_block(c2, 2 * t + 5);
+    scan_two_blocks(p0, p1, r0, r1, D1, D2, 2 * t + 2, best1, bg1, best2, bg2);
   }
-  if (groups & 1) {
+  if (t < pairs) {  // an odd number of block pairs: set A holds the last one
+    const Block4 n0 = load_block(c1, 2 * t + 2), m0 = load_block(c2, 2 * t + 2);
+    scan_two_blocks(a0, a1, e0, e1, D1, D2, 2 * t, best1, bg1, best2, bg2);
+    a0 = n0;
+    e0 = m0;
+  }
+  if (groups & 1) {  // a0 / e0 hold the last block
     float da[4], dc[4];
     dots4(a0, D1, da);
     dots4(e0, D2, dc);

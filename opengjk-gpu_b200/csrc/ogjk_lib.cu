@@ -1447,6 +1447,7 @@ extern "C" {
 
 const char* ogjk_last_error(void) { return t_err.c_str(); }
 const char* ogjk_version(void) { return "opengjk-b200 0.1 (sm_100a)"; }
+int ogjk_selected_device_count(void) { return (int)selected_devices().size(); }
 int ogjk_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;

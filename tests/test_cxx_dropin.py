@@ -27,11 +27,16 @@ def test_reference_style_caller_compiles_and_links(pkg, flag):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["", "0,0"])  # "0,0": the fan-out path of GJK::GPU::compute* (device 0 listed twice)
 @pytest.mark.parametrize("flag", ["", "-DOGJK_USE_64BITS"])
-def test_reference_style_caller_prints_readme_outputs(pkg, flag):
+def test_reference_style_caller_prints_readme_outputs(pkg, flag, devices):
     pkg.load_library()
     exe = _build(flag)
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    env = dict(os.environ)
+    env.pop("OGJK_DEVICES", None)
+    if devices:
+        env["OGJK_DEVICES"] = devices
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     text = out.stdout
     # reference README.md:111-115
