@@ -258,10 +258,15 @@ class Runner:
 
     @staticmethod
     def mismatches(simp, dist, nrm, es, ed, en):
-        bad = dist != ed
-        bad |= (nrm != en).any(axis=1)
+        """pairs whose outputs differ from the reference's in any BIT (so -0.0 against +0.0 counts, and a NaN only matches
+        the same NaN)"""
+        def bits(x):
+            x = np.ascontiguousarray(x)
+            return x.view(np.uint32 if x.dtype.itemsize == 4 else np.uint64)
+        bad = bits(dist) != bits(ed)
+        bad |= (bits(nrm) != bits(en)).any(axis=1)
         bad |= simp["nvrtx"] != es["nvrtx"]
-        bad |= (simp["witnesses"] != es["witnesses"]).reshape(len(ed), -1).any(axis=1)
+        bad |= (bits(simp["witnesses"]) != bits(es["witnesses"])).reshape(len(ed), -1).any(axis=1)
         return int(bad.sum())
 
     # ---- dense workloads (cfg2, cfg3): weak scaling --------------------------------------------------------------

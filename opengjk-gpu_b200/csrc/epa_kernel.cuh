@@ -212,12 +212,18 @@ OGJK_D uint32_t make_face(WT& W, int f, int a, int b, int c, const V3<typename W
   using T = typename WT::real;
   const V3<T> va = work_vertex(W, a), vb = work_vertex(W, b), vc = work_vertex(W, c);
   const V3<T> e0 = vsub(vb, va), e1 = vsub(vc, va);
-  V3<T> nrm = cross(e0, e1);
-  if (dot(nrm, vsub(centroid, va)) > T(0)) {  // swap corners 1 and 2; the raw normal flips sign exactly
+  // cross(e0, e1) = (p - q) per component; after a swap of corners 1 and 2 the reference recomputes cross(e1, e0) =
+  // (q - p) from the same products (EPA.c:92-129 after :203-232 / :791-819).  That is the exact negative EXCEPT for a
+  // component that cancels to zero: p - p = +0 either way, where a negation would give -0.
+  const T px = mul_rn(e0.y, e1.z), qx = mul_rn(e0.z, e1.y);
+  const T py = mul_rn(e0.z, e1.x), qy = mul_rn(e0.x, e1.z);
+  const T pz = mul_rn(e0.x, e1.y), qz = mul_rn(e0.y, e1.x);
+  V3<T> nrm = mk<T>(sub_rn(px, qx), sub_rn(py, qy), sub_rn(pz, qz));
+  if (dot(nrm, vsub(centroid, va)) > T(0)) {  // swap corners 1 and 2
     const int t = b;
     b = c;
     c = t;
-    nrm = vneg(nrm);
+    nrm = mk<T>(sub_rn(qx, px), sub_rn(qy, py), sub_rn(qz, pz));
   }
   const T len2 = norm2(nrm);
   const T eps = Tol<T>::eps();

@@ -43,16 +43,33 @@ def host_harness():
     return ctypes.CDLL(out)
 
 
+def _same(got, want):
+    """float arrays equal as BIT PATTERNS (so -0.0 differs from +0.0); two NaNs match whatever their payload (the CPU and
+    the GPU generate different default NaNs)"""
+    got, want = np.ascontiguousarray(got), np.ascontiguousarray(want)
+    u = np.uint32 if got.dtype.itemsize == 4 else np.uint64
+    return bool(np.all((got.view(u) == want.view(u)) | (np.isnan(got) & np.isnan(want))))
+
+
 def live_simplex_equal(got, want):
-    """gkSimplex equality on what is defined: nvrtx, the live slots, the witnesses."""
+    """gkSimplex equality on what is defined: nvrtx, the live slots, the witnesses -- floats as bit patterns."""
     if not np.array_equal(got["nvrtx"], want["nvrtx"]):
         return False
-    if not np.array_equal(got["witnesses"], want["witnesses"], equal_nan=True):
+    if not _same(got["witnesses"], want["witnesses"]):
         return False
     for j in range(4):
         live = want["nvrtx"] > j
-        if not np.array_equal(got["vrtx"][live, j], want["vrtx"][live, j], equal_nan=True):
+        if not _same(got["vrtx"][live, j], want["vrtx"][live, j]):
             return False
         if not np.array_equal(got["vrtx_idx"][live, j], want["vrtx_idx"][live, j]):
             return False
     return True
+
+
+def same_bits(got, want):
+    """bit-pattern equality of two float arrays: -0.0 differs from +0.0, a NaN only matches the same NaN"""
+    got, want = np.ascontiguousarray(got), np.ascontiguousarray(want)
+    if got.shape != want.shape or got.dtype != want.dtype:
+        return False
+    u = np.uint32 if got.dtype.itemsize == 4 else np.uint64
+    return bool(np.array_equal(got.view(u), want.view(u)))

@@ -1,4 +1,6 @@
 """GPU parity: EPA (penetration depth, witnesses, contact normal) against the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -140,3 +142,51 @@ def test_small_work_area_overflow_is_exercised(pkg, oracle_mod):
     s, d = orc.gjk(a, b, nthreads=8)
     _s, _d, _n, it = orc.epa(a, b, s, d, nthreads=8, want_iters=True)
     assert (it > 26).sum() >= 3
+
+
+@pytest.mark.parametrize("kernel", ["auto", "warp", "small4", "small8", "group"])
+def test_sign_of_zero_on_lattice_cubes(pkg, oracle_mod, kernel):
+    """Axis-aligned cubes on a quarter-integer lattice (and the README's rotated cube): face normals are full of exact
+    zeros, a sixth of them negative (the reference's README prints `-0.000000` for one).  Outputs must match the reference as BIT PATTERNS --
+    np.array_equal alone would accept +0.0 for -0.0.  (Caught a shared-reciprocal division whose correction step turned
+    -0 / len into +0.)"""
+    from conftest import same_bits
+    import torch
+    dtype = np.float32
+    rng = np.random.Generator(np.random.Philox(key=[41, 7]))
+    n = 40000
+    cube = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], dtype=np.float64)
+    a = cube[np.argsort(rng.random((n, 8)), axis=1)]  # the corners in a random order per pair
+    perm = np.argsort(rng.random((n, 8)), axis=1)
+    rot = pkg.workloads.rotated_cube_readme(np.float64) - np.array([1.0, 0.0, 0.0])
+    half = n // 2
+    b = np.empty((n, 8, 3))
+    b[:half] = cube[perm[:half]] + rng.integers(-6, 7, size=(half, 1, 3)) * 0.25
+    b[half:] = rot[perm[half:]] + rng.integers(-6, 7, size=(n - half, 1, 3)) * 0.25
+    a, b = np.ascontiguousarray(a.astype(dtype)), np.ascontiguousarray(b.astype(dtype))
+    orc = oracle_mod.Oracle("ref" if oracle_mod.available("ref", dtype) else "port", dtype)
+    s, d = orc.gjk(a, b, nthreads=8)
+    es, ed, en = orc.epa(a, b, s, d, nthreads=8)
+    assert np.signbit(en[en == 0]).any(), "the case is meant to contain negative zeros"
+    eng = pkg.Engine(dtype)
+    d_a, d_b = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    d_simp = torch.zeros(n * eng.sdtype.itemsize, dtype=torch.uint8, device="cuda")
+    d_dist = torch.zeros(n, dtype=torch.float32, device="cuda")
+    d_nrm = torch.zeros(n, 3, dtype=torch.float32, device="cuda")
+    saved = os.environ.get("OGJK_EPA_KERNEL")
+    try:
+        if kernel == "auto":
+            os.environ.pop("OGJK_EPA_KERNEL", None)
+        else:
+            os.environ["OGJK_EPA_KERNEL"] = kernel
+        eng.gjk_epa_uniform_device(n, 8, d_a, 8, d_b, d_simp, d_dist, d_nrm)
+        torch.cuda.synchronize()
+    finally:
+        if saved is None:
+            os.environ.pop("OGJK_EPA_KERNEL", None)
+        else:
+            os.environ["OGJK_EPA_KERNEL"] = saved
+    got = d_simp.cpu().numpy().view(eng.sdtype)
+    assert same_bits(d_dist.cpu().numpy(), ed)
+    assert same_bits(d_nrm.cpu().numpy(), en)
+    assert same_bits(got["witnesses"], es["witnesses"])

@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import live_simplex_equal
+from conftest import live_simplex_equal, same_bits
 from golden_util import assert_matches_golden, golden_cases
 
 pytestmark = pytest.mark.gpu
@@ -33,6 +33,11 @@ def _assert_same(tag, got_simp, got_dist, got_nrm, want_simp, want_dist, want_nr
         bad = np.flatnonzero((got_nrm != want_nrm).any(axis=1))
         assert bad.size == 0, f"{tag}: {bad.size} normal mismatches, first at pair {bad[:5]}"
     assert live_simplex_equal(got_simp, want_simp), f"{tag}: simplex / witness mismatch"
+    # and as bit patterns: the sign of a zero component is part of the reference's output too
+    assert same_bits(got_dist, want_dist), f"{tag}: distances equal as values but not as bits"
+    if want_nrm is not None:
+        assert same_bits(got_nrm, want_nrm), f"{tag}: normals equal as values but not as bits"
+    assert same_bits(got_simp["witnesses"], want_simp["witnesses"]), f"{tag}: witnesses equal as values but not as bits"
 
 
 def _device_gjk_epa(pkg, a, b, dtype):
