@@ -697,24 +697,38 @@ bool lookup_pool(const void* d_desc, PoolInfo* out) {
 // against it on the device (one pass over `count` descriptors, a 4-byte read-back).  *ok = false sends the call to
 // the descriptor-reading general kernels, so a caller that edits d_bd[i].coord / numpoints after upload, or re-uses
 // a freed address without telling the library, still gets results for the descriptors it passed.
+// One or two descriptor arrays per call share one flag, one read-back (into pinned host memory) and one synchronisation:
+// on small batches the check is most of what the call costs.
+thread_local int* t_pinned_flag = nullptr;
 template <typename T>
-int pool_layout_holds(const void* d_desc, const PoolInfo& info, int count, bool* ok) {
+int pool_layouts_hold(const void* d_desc1, const PoolInfo& info1, const void* d_desc2, const PoolInfo* info2, int count,
+                      bool* ok) {
   *ok = false;
-  if (info.nv <= 0 || count > info.count) return 0;
+  if (info1.nv <= 0 || count > info1.count) return 0;
+  if (d_desc2 && (info2->nv <= 0 || count > info2->count)) return 0;
   StreamScratch* ss = nullptr;
   if (int rc = stream_scratch(&ss)) return rc;
   int* flag = nullptr;
   if (int rc = scratch_grow(ss->flag, 1, &flag)) return rc;
+  if (!t_pinned_flag) OGJK_CK(cudaMallocHost(&t_pinned_flag, sizeof(int)));
   OGJK_CK(cudaMemsetAsync(flag, 0, sizeof(int), t_stream));
-  validate_dense_kernel<T><<<(unsigned)((count + 255) / 256), 256, 0, t_stream>>>((const PolytopeT<T>*)d_desc, count,
-                                                                                 (const T*)info.coords, info.nv, flag);
+  const unsigned grid = (unsigned)((count + 255) / 256);
+  validate_dense_kernel<T><<<grid, 256, 0, t_stream>>>((const PolytopeT<T>*)d_desc1, count, (const T*)info1.coords, info1.nv, flag);
   ++t_launches;
+  if (d_desc2) {
+    validate_dense_kernel<T><<<grid, 256, 0, t_stream>>>((const PolytopeT<T>*)d_desc2, count, (const T*)info2->coords, info2->nv, flag);
+    ++t_launches;
+  }
   OGJK_CK(cudaGetLastError());
-  int h = 1;
-  OGJK_CK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, t_stream));
+  *t_pinned_flag = 1;
+  OGJK_CK(cudaMemcpyAsync(t_pinned_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, t_stream));
   OGJK_CK(cudaStreamSynchronize(t_stream));
-  *ok = h == 0;
+  *ok = *t_pinned_flag == 0;
   return 0;
+}
+template <typename T>
+int pool_layout_holds(const void* d_desc, const PoolInfo& info, int count, bool* ok) {
+  return pool_layouts_hold<T>(d_desc, info, nullptr, nullptr, count, ok);
 }
 
 // GJK (and optionally the fused EPA gate + EPA) over `pairs` into a uniform fp32 pool.  Returns 1 when the batch does
@@ -1523,6 +1537,10 @@ int ogjk_set_devices(int count, const int* devices) {
 }
 int ogjk_release_cached_buffers(void) {
   // buffers cached by the calling thread on every device: host-path staging pools + scratch (kernels must be idle)
+  if (t_pinned_flag) {
+    cudaFreeHost(t_pinned_flag);
+    t_pinned_flag = nullptr;
+  }
   int cur = 0;
   OGJK_CK(cudaGetDevice(&cur));
   for (int d = 0; d < kMaxDevices; ++d) {
@@ -1645,11 +1663,9 @@ long long ogjk_launch_count(int reset) {
     PoolInfo p1, p2;                                                                                                   \
     const bool known = lookup_pool(d_bd1, &p1) && lookup_pool(d_bd2, &p2) && p1.count >= n && p2.count >= n;           \
     if (known && p1.nv > 0 && p2.nv > 0) { /* arrays uploaded by allocate_and_copy_device_arrays, uniform + dense */   \
-      bool ok1 = false, ok2 = false;                                                                                   \
-      if (int rc = pool_layout_holds<REAL>(d_bd1, p1, n, &ok1)) return rc;                                             \
-      if (ok1)                                                                                                         \
-        if (int rc = pool_layout_holds<REAL>(d_bd2, p2, n, &ok2)) return rc;                                           \
-      if (ok1 && ok2) {                                                                                                \
+      bool ok = false;                                                                                                 \
+      if (int rc = pool_layouts_hold<REAL>(d_bd1, p1, d_bd2, &p2, n, &ok)) return rc;                                  \
+      if (ok) {                                                                                                        \
         const int fast = launch_gjk_uniform<REAL>(n, p1.nv, (const REAL*)p1.coords, p2.nv, (const REAL*)p2.coords,     \
                                                   (SimplexT<REAL>*)d_simplices, d_distances);                          \
         if (fast <= 0) return fast;                                                                                    \

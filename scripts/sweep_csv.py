@@ -21,35 +21,48 @@ PUBLISHED_4070 = {  # (polytopes, vertices): (GPU_ms, CPU_ms), reference data/da
 CASES = [(1000, v) for v in (50, 100, 200, 500, 1000, 5000)] + [(n, 500) for n in (50, 100, 250, 500, 1000, 5000, 10000, 50000)]
 RUNS = 10
 
-def main(out):
+def main(out, cases=None, runs=RUNS, plot_out=None, check=False):
+    """writes `out` in the format of GJK::GPU::testing (example.cu:281, 376) and, when `plot_out` is given, the same rows
+    in the column layout of the published data file the reference's plotting/create_plots.py reads (data/data_32bit_4070:
+    polytopes,Vertices,GPU_ms,CPU_ms).  check=True compares every run's distances with the CPU result, bit for bit."""
+    cases = cases or CASES
     pkg = load_package()
     om = load_oracle()
     orc = om.Oracle("ref" if om.available("ref", np.float32) else "port", np.float32)
     eng = pkg.Engine(np.float32); eng.set_device(0); eng.set_sync(False)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     rows = ["NumPolytopes,NumVertices,CPU_Time_ms,GPU_Time_ms"]
+    prow = ["polytopes,Vertices,GPU_ms,CPU_ms"]
     print(f"{'pairs':>7} {'verts':>6} {'CPU ms':>10} {'GPU ms':>9} {'speed-up':>9}   published RTX 4070: GPU ms / CPU ms / speed-up")
-    for n, nv in CASES:
+    for n, nv in cases:
         cpu_sum = gpu_sum = 0.0
-        for run in range(RUNS):
+        for run in range(runs):
             a, b = pkg.workloads.random_pairs(n, nv, 10.0, seed=1000 * run + nv + n, dtype=np.float32)
             bd1, _k1 = pkg.make_polytopes(a); bd2, _k2 = pkg.make_polytopes(b)
             h = eng.allocate_and_copy_device_arrays(bd1, bd2)
             d_bd1, d_bd2, d_c1, d_c2, d_simp, d_dist = h
             if run == 0:
                 eng.compute_minimum_distance_device(n, d_bd1, d_bd2, d_simp, d_dist); torch.cuda.synchronize()
-            t0 = time.perf_counter(); orc.gjk(a, b, nthreads=1); cpu_sum += (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter(); cs, cd = orc.gjk(a, b, nthreads=1); cpu_sum += (time.perf_counter() - t0) * 1e3
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(); eng.compute_minimum_distance_device(n, d_bd1, d_bd2, d_simp, d_dist); e1.record()
             torch.cuda.synchronize(); gpu_sum += e0.elapsed_time(e1)
+            if check:
+                gs, gd = eng.copy_results_from_device(n, d_simp, d_dist)
+                assert np.array_equal(gd.view(np.uint32), cd.view(np.uint32)), f"{n} x {nv}: distances differ from the CPU run"
             eng.free_device_arrays(*h)
-        cpu, gpu = cpu_sum / RUNS, gpu_sum / RUNS
+        cpu, gpu = cpu_sum / runs, gpu_sum / runs
         rows.append(f"{n},{nv},{cpu:.6f},{gpu:.6f}")
+        prow.append(f"{n},{nv},{gpu:.4f},{cpu:.4f}")
         pub = PUBLISHED_4070.get((n, nv))
         ptxt = f"{pub[0]:.4f} / {pub[1]:.4f} / {pub[1] / pub[0]:.1f}x" if pub else ""
         print(f"{n:7d} {nv:6d} {cpu:10.4f} {gpu:9.4f} {cpu / gpu:8.1f}x   {ptxt}", flush=True)
     open(out, "w").write("\n".join(rows) + "\n")
-    print("wrote", out)
+    if plot_out:
+        open(plot_out, "w").write("\n".join(prow) + "\n")
+    print("wrote", out, plot_out or "")
+    return rows, prow
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/data_32bit_b200.csv")
+    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/data_32bit_b200.csv",
+         plot_out=sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/data_32bit_b200_plot_format.csv")
