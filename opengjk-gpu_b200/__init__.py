@@ -253,12 +253,18 @@ class Engine:
                    _ptr(simplices), _ptr(distances), _ptr(nrm))
         return simplices, distances, nrm
 
-    def compute_gjk_epa_indexed(self, polytopes, pairs):
+    def compute_gjk_epa_indexed(self, polytopes, pairs, out=None):
+        """`out` = (simplices, distances, normals) arrays to write into (e.g. views of pinned memory); allocated when None"""
         pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
         n = pairs.shape[0]
-        simplices = np.zeros(n, self.sdtype)
-        distances = np.zeros(n, self.dtype)
-        nrm = np.zeros((n, 3), self.dtype)
+        if out is not None:
+            simplices, distances, nrm = out
+            assert simplices.shape == (n,) and simplices.dtype == self.sdtype and distances.shape == (n,)
+            assert nrm.shape == (n, 3) and distances.dtype == self.dtype and nrm.dtype == self.dtype
+        else:
+            simplices = np.zeros(n, self.sdtype)
+            distances = np.zeros(n, self.dtype)
+            nrm = np.zeros((n, 3), self.dtype)
         self._call("compute_gjk_epa_indexed", ctypes.c_int(len(polytopes)), ctypes.c_int(n), _ptr(polytopes),
                    _ptr(pairs), _ptr(simplices), _ptr(distances), _ptr(nrm))
         return simplices, distances, nrm

@@ -902,7 +902,7 @@ enum Stage : int { kGjk = 1, kEpa = 2 };
 // ---- cached device buffers + helper streams for the host-pointer fast path -----------------------------------
 // The reference allocates and frees six device buffers on every high-level call (openGJK.cu:2889-2954, 3034-3048).
 // Here they are grow-only per (thread, device) and re-used, so a steady-state call costs no cudaMalloc/cudaFree.
-enum Slot : int { kSlotC1 = 0, kSlotC2, kSlotSimp, kSlotDist, kSlotNrm, kSlotCount };
+enum Slot : int { kSlotC1 = 0, kSlotC2, kSlotSimp, kSlotDist, kSlotNrm, kSlotPairs, kSlotCount };
 struct DevicePool {
   void* ptr[kSlotCount] = {};
   size_t cap[kSlotCount] = {};
@@ -1135,62 +1135,100 @@ int run_pairs_host(int n, const PolytopeT<T>* bd1, const PolytopeT<T>* bd2, Simp
 template <typename T>
 int run_indexed_host(int num_polytopes, int num_pairs, const PolytopeT<T>* polytopes, const CollisionPair* pairs,
                      SimplexT<T>* simplices, T* distances, T* normals, int stages) {
+  // Host-level indexed call (reference openGJK.cu:3274-3311: upload pool + pair list, launch, copy everything back).
+  // Here the pair list is processed in chunks of ~1 Mi pairs through pooled device buffers: the pair records of chunk
+  // k+1 go up and the results of chunk k-1 come down (124 bytes per pair -- the dominant transfer of this call) while
+  // the kernels of chunk k run; nothing is allocated per call except the (small) pool.
   if (num_pairs <= 0 || num_polytopes <= 0) return 0;
   if (!polytopes || !pairs || !simplices || !distances) return fail_msg("null argument");
-  Flattened<T> pool;
+  const size_t np = (size_t)num_pairs;
+  int dev = 0;
+  OGJK_CK(cudaGetDevice(&dev));
+  DevicePool& P = t_pool[dev];
   CollisionPair* d_pairs = nullptr;
   SimplexT<T>* d_simp = nullptr;
   T* d_dist = nullptr;
   T* d_nrm = nullptr;
+  if (int rc = pool_get(P, kSlotPairs, np * sizeof(CollisionPair), (void**)&d_pairs)) return rc;
+  if (int rc = pool_get(P, kSlotSimp, np * sizeof(SimplexT<T>), (void**)&d_simp)) return rc;
+  if (int rc = pool_get(P, kSlotDist, np * sizeof(T), (void**)&d_dist)) return rc;
+  if (stages & kEpa)
+    if (int rc = pool_get(P, kSlotNrm, np * 3 * sizeof(T), (void**)&d_nrm)) return rc;
+  size_t chunks = (np + (1u << 20) - 1) >> 20;
+  size_t chunk_pairs = ((np + chunks - 1) / chunks + 255) & ~(size_t)255;  // equal chunks, all large enough for the slot kernels
+  if (int rc = pool_streams(P, chunks)) return rc;
+  Flattened<T> pool;
+  if (int rc = flatten_upload(num_polytopes, polytopes, pool)) {
+    release(pool);
+    return rc;
+  }
   int rc = 0;
-  cudaError_t e;
-  const size_t np = (size_t)num_pairs;
-  do {
-    for (size_t i = 0; i < np; ++i)
-      if (pairs[i].idx1 < 0 || pairs[i].idx1 >= num_polytopes || pairs[i].idx2 < 0 || pairs[i].idx2 >= num_polytopes) {
-        rc = fail_msg("pair index out of range");
+  {
+    // order the pool's streams after the upload of the polytope pool (queued on the selected stream)
+    cudaEventRecord(P.ev_done[0], t_stream);
+    cudaStreamWaitEvent(P.s_copy, P.ev_done[0], 0);
+    cudaStreamWaitEvent(P.s_comp, P.ev_done[0], 0);
+    cudaStreamWaitEvent(P.s_out, P.ev_done[0], 0);
+    struct Drain {  // every exit leaves no copy to or from the caller's arrays in flight
+      DevicePool& p;
+      ~Drain() {
+        cudaStreamSynchronize(p.s_copy);
+        cudaStreamSynchronize(p.s_comp);
+        cudaStreamSynchronize(p.s_out);
+      }
+    } drain{P};
+    SyncOverride nosync;
+    const PoolInfo info{pool.d_coord, pool.uniform_nv, num_polytopes, (int)pool.max_nv};
+    for (size_t k = 0; k < chunks && !rc; ++k) {
+      const size_t lo = k * chunk_pairs;
+      if (lo >= np) break;
+      const size_t m = np - lo < chunk_pairs ? np - lo : chunk_pairs;
+      for (size_t i = lo; i < lo + m; ++i)
+        if (pairs[i].idx1 < 0 || pairs[i].idx1 >= num_polytopes || pairs[i].idx2 < 0 || pairs[i].idx2 >= num_polytopes) {
+          rc = fail_msg("pair index out of range");
+          break;
+        }
+      if (rc) break;
+      cudaError_t e = cudaMemcpyAsync(d_pairs + lo, pairs + lo, m * sizeof(CollisionPair), cudaMemcpyHostToDevice, P.s_copy);
+      if (e == cudaSuccess && !(stages & kGjk)) {  // EPA alone: simplices and distances are inputs
+        e = cudaMemcpyAsync(d_simp + lo, simplices + lo, m * sizeof(SimplexT<T>), cudaMemcpyHostToDevice, P.s_copy);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dist + lo, distances + lo, m * sizeof(T), cudaMemcpyHostToDevice, P.s_copy);
+      }
+      if (e == cudaSuccess) e = cudaEventRecord(P.ev_in[k], P.s_copy);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(P.s_comp, P.ev_in[k], 0);
+      if (e != cudaSuccess) {
+        rc = fail("H2D pairs", e);
         break;
       }
-    if (rc) break;
-    if ((rc = flatten_upload(num_polytopes, polytopes, pool))) break;
-    if ((e = cudaMalloc(&d_pairs, np * sizeof(CollisionPair))) != cudaSuccess) { rc = fail("cudaMalloc(pairs)", e); break; }
-    if ((e = cudaMalloc(&d_simp, np * sizeof(SimplexT<T>))) != cudaSuccess) { rc = fail("cudaMalloc(simplices)", e); break; }
-    if ((e = cudaMalloc(&d_dist, np * sizeof(T))) != cudaSuccess) { rc = fail("cudaMalloc(distances)", e); break; }
-    if ((e = cudaMemcpyAsync(d_pairs, pairs, np * sizeof(CollisionPair), cudaMemcpyHostToDevice, t_stream)) != cudaSuccess) { rc = fail("H2D pairs", e); break; }
-    if (stages & kEpa) {
-      if ((e = cudaMalloc(&d_nrm, np * 3 * sizeof(T))) != cudaSuccess) { rc = fail("cudaMalloc(normals)", e); break; }
-      if ((e = cudaMemsetAsync(d_nrm, 0, np * 3 * sizeof(T), t_stream)) != cudaSuccess) { rc = fail("memset", e); break; }
-    }
-    if (stages & kGjk) {
-      if ((e = cudaMemsetAsync(d_simp, 0, np * sizeof(SimplexT<T>), t_stream)) != cudaSuccess) { rc = fail("memset", e); break; }
-    } else {
-      if ((e = cudaMemcpyAsync(d_simp, simplices, np * sizeof(SimplexT<T>), cudaMemcpyHostToDevice, t_stream)) != cudaSuccess) { rc = fail("H2D simplices", e); break; }
-      if ((e = cudaMemcpyAsync(d_dist, distances, np * sizeof(T), cudaMemcpyHostToDevice, t_stream)) != cudaSuccess) { rc = fail("H2D distances", e); break; }
-    }
-    {
-      SyncOverride nosync;
-      IndexedSource<T> src{pool.d_desc, d_pairs};
-      const PoolInfo info{pool.d_coord, pool.uniform_nv, num_polytopes, (int)pool.max_nv};
-      rc = launch_indexed_uniform<T>(num_pairs, info, d_pairs, pool.d_desc, d_simp, d_dist, d_nrm, stages);
-      if (rc < 0 || (rc != 0 && rc != 1)) break;
-      if (rc == 1) {  // not a uniform fp32 pool / small batch: the general kernels
-        rc = 0;
-        if ((stages & kGjk) && (rc = launch_gjk_generic<T>(src, num_pairs, (int)pool.max_nv, d_simp, d_dist))) break;
-        if ((stages & kEpa) && (rc = launch_epa<T>(src, num_pairs, (int)pool.max_nv, d_simp, d_dist, d_nrm))) break;
+      {
+        StreamOverride on(P.s_comp);
+        if (stages & kEpa) cudaMemsetAsync(d_nrm + 3 * lo, 0, m * 3 * sizeof(T), P.s_comp);
+        if (stages & kGjk) cudaMemsetAsync(d_simp + lo, 0, m * sizeof(SimplexT<T>), P.s_comp);
+        IndexedSource<T> src{pool.d_desc, d_pairs + lo};
+        rc = launch_indexed_uniform<T>((int)m, info, d_pairs + lo, pool.d_desc, d_simp + lo, d_dist + lo,
+                                       d_nrm ? d_nrm + 3 * lo : nullptr, stages);
+        if (rc == 1) {  // not a uniform fp32 pool / small batch: the general kernels
+          rc = 0;
+          if (stages & kGjk) rc = launch_gjk_generic<T>(src, (int)m, (int)pool.max_nv, d_simp + lo, d_dist + lo);
+          if (!rc && (stages & kEpa)) rc = launch_epa<T>(src, (int)m, (int)pool.max_nv, d_simp + lo, d_dist + lo, d_nrm + 3 * lo);
+        }
       }
+      if (rc) break;
+      e = cudaEventRecord(P.ev_done[k], P.s_comp);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(P.s_out, P.ev_done[k], 0);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(simplices + lo, d_simp + lo, m * sizeof(SimplexT<T>), cudaMemcpyDeviceToHost, P.s_out);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(distances + lo, d_dist + lo, m * sizeof(T), cudaMemcpyDeviceToHost, P.s_out);
+      if (e == cudaSuccess && (stages & kEpa) && normals)
+        e = cudaMemcpyAsync(normals + 3 * lo, d_nrm + 3 * lo, m * 3 * sizeof(T), cudaMemcpyDeviceToHost, P.s_out);
+      if (e != cudaSuccess) rc = fail("D2H results", e);
     }
-    if ((e = cudaMemcpyAsync(simplices, d_simp, np * sizeof(SimplexT<T>), cudaMemcpyDeviceToHost, t_stream)) != cudaSuccess) { rc = fail("D2H simplices", e); break; }
-    if ((e = cudaMemcpyAsync(distances, d_dist, np * sizeof(T), cudaMemcpyDeviceToHost, t_stream)) != cudaSuccess) { rc = fail("D2H distances", e); break; }
-    if ((stages & kEpa) && normals) {
-      if ((e = cudaMemcpyAsync(normals, d_nrm, np * 3 * sizeof(T), cudaMemcpyDeviceToHost, t_stream)) != cudaSuccess) { rc = fail("D2H normals", e); break; }
+    if (!rc) {
+      cudaError_t e = cudaStreamSynchronize(P.s_out);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(P.s_comp);
+      if (e != cudaSuccess) rc = fail("indexed host call", e);
     }
-    if ((e = cudaStreamSynchronize(t_stream)) != cudaSuccess) { rc = fail("sync", e); break; }
-  } while (0);
+  }
   release(pool);
-  cudaFree(d_pairs);
-  cudaFree(d_simp);
-  cudaFree(d_dist);
-  cudaFree(d_nrm);
   return rc;
 }
 
