@@ -570,7 +570,7 @@ def ours(args):
             if other == name:
                 continue
             try:
-                r = R.cfg5(xs, 3, False, R.world == 1) if other == "cfg5" else R.dense(other, xs, 3, False, R.world == 1)
+                r = R.cfg5(xs, 3, True, R.world == 1) if other == "cfg5" else R.dense(other, xs, 3, True, R.world == 1)
                 r["ms_per_step"] = r["total_ms"] / xs
                 r["steps"] = xs
                 r["scaling"] = "strong" if other == "cfg5" else "weak"
