@@ -193,7 +193,7 @@ template <typename T, int G, int KV, typename WT, int MINB, typename Source>
 __global__ void __launch_bounds__(EpaGroupConfig<T>::kThreads, MINB)
 epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
                  T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters,
-                 int* __restrict__ overflow) {
+                 int* __restrict__ overflow, int svc_batch, int svc_defer, int hz_compact) {
   extern __shared__ __align__(16) unsigned char epa_smem[];
   WT* work = reinterpret_cast<WT*>(epa_smem);
   const int wlane = threadIdx.x & 31;
@@ -220,9 +220,52 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
   int report_face = -1;
   T report_d = T(0);
 
+  // Reporting a finished pair (lane 0 of its group, ~300 instructions) and setting up the next one (~500) run while the
+  // other seven groups of the warp wait.  They are therefore BATCHED: a group that has finished waits until `svc_batch`
+  // groups need service, or `svc_defer` expansion steps have passed, or nothing is expanding -- the service code then
+  // runs once for all of them.
+  int deferred = 0;
   for (;;) {
+    bool service;
+    {
+      const unsigned need = __ballot_sync(0xffffffffu, phase == kIdle || phase == kReport);
+      const unsigned busy = __ballot_sync(0xffffffffu, phase == kExpand);
+      service = need != 0u && (busy == 0u || __popc(need) >= svc_batch * G || deferred >= svc_defer);
+      deferred = service ? 0 : (need != 0u ? deferred + 1 : 0);
+    }
+    // ================================ outputs ======================================================================
+    if (service && phase == kReport) {
+      if (g.lane == 0) {
+        if (nv_in != 4) {  // the regrown simplex is part of the result (EPA.c modifies it in place)
+          sp->nvrtx = 4;
+          for (int j = nv_in < 0 ? 0 : nv_in; j < 4; ++j) {
+            sp->vrtx[j][0] = W.vx[j]; sp->vrtx[j][1] = W.vy[j]; sp->vrtx[j][2] = W.vz[j];
+            sp->vrtx_idx[j][0] = W.src1[j]; sp->vrtx_idx[j][1] = W.src2[j];
+          }
+        }
+        if (reported) {  // EPA.c:636-651
+          const uint32_t word = W.fv[report_face];
+          const int a = word & 0xff, b = (word >> 8) & 0xff, c = (word >> 16) & 0xff;
+          T a0, a1, a2;
+          origin_barycentric(work_vertex(W, a), work_vertex(W, b), work_vertex(W, c), a0, a1, a2);
+          const V3<T> pa = load3(A.c, W.src1[a]), pb = load3(A.c, W.src1[b]), pc = load3(A.c, W.src1[c]);
+          const V3<T> qa = load3(B.c, W.src2[a]), qb = load3(B.c, W.src2[b]), qc = load3(B.c, W.src2[c]);
+          sp->witnesses[0][0] = add_rn(add_rn(mul_rn(pa.x, a0), mul_rn(pb.x, a1)), mul_rn(pc.x, a2));
+          sp->witnesses[0][1] = add_rn(add_rn(mul_rn(pa.y, a0), mul_rn(pb.y, a1)), mul_rn(pc.y, a2));
+          sp->witnesses[0][2] = add_rn(add_rn(mul_rn(pa.z, a0), mul_rn(pb.z, a1)), mul_rn(pc.z, a2));
+          sp->witnesses[1][0] = add_rn(add_rn(mul_rn(qa.x, a0), mul_rn(qb.x, a1)), mul_rn(qc.x, a2));
+          sp->witnesses[1][1] = add_rn(add_rn(mul_rn(qa.y, a0), mul_rn(qb.y, a1)), mul_rn(qc.y, a2));
+          sp->witnesses[1][2] = add_rn(add_rn(mul_rn(qa.z, a0), mul_rn(qb.z, a1)), mul_rn(qc.z, a2));
+          nrm_out[0] = W.nx[report_face];
+          nrm_out[1] = W.ny[report_face];
+          nrm_out[2] = W.nz[report_face];
+          distances[pair] = -report_d;
+        }
+      }
+      phase = kIdle;
+    }
     // ================================ fetch + set up the next pair =================================================
-    if (phase == kIdle) {
+    if (service && phase == kIdle) {
       int q = 0;
       if (g.lane == 0) q = atomicAdd(&counters[1], 1);
       q = g.bcast(q, 0);
@@ -542,6 +585,31 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
           const int q2 = base_rank + __popc(keepm & g.below());
           if (q2 < nfree) {
             const int slot = free_slot(q2);
+            if (hz_compact) {
+              W.fv[slot] = key;  // parked in its (free: live byte 0) slot until the face pass below
+            } else {
+              const int lo = (int)(key & 0xffu), hi8 = (int)((key >> 8) & 0x7fu);
+              const bool rev = (key & 0x8000u) != 0u;
+              bool degenerate = false;
+              const uint32_t word = make_face(W, slot, rev ? hi8 : lo, rev ? lo : hi8, newv, centroid, degenerate);
+              W.fv[slot] = word;
+              if (degenerate) any_degenerate = true;
+            }
+          }
+        }
+        base_rank += __popc(keepm);
+      }
+      if (hz_compact) {
+        // The horizon edges are now parked one per new slot, in rank order: build the faces in a second pass whose trip
+        // count is the number of NEW faces (dying faces + 2) instead of the number of dying-face edges (3 per face).
+        const int used_now = base_rank < nfree ? base_rank : nfree;
+        const int usedw = __reduce_max_sync(0xffffffffu, used_now);
+        __syncwarp();
+        for (int r0 = 0; r0 < usedw; r0 += G) {
+          const int r = r0 + g.lane;
+          if (r < used_now) {
+            const int slot = free_slot(r);
+            const uint32_t key = W.fv[slot];
             const int lo = (int)(key & 0xffu), hi8 = (int)((key >> 8) & 0x7fu);
             const bool rev = (key & 0x8000u) != 0u;
             bool degenerate = false;
@@ -550,7 +618,6 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
             if (degenerate) any_degenerate = true;
           }
         }
-        base_rank += __popc(keepm);
       }
       if (WT::kSmall && act && base_rank > nfree) {  // ran out of the small area's face slots: the full-size area has more
         ovf = true;
@@ -581,37 +648,6 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
       }
     }
 
-    // ================================ outputs ======================================================================
-    if (phase == kReport) {
-      if (g.lane == 0) {
-        if (nv_in != 4) {  // the regrown simplex is part of the result (EPA.c modifies it in place)
-          sp->nvrtx = 4;
-          for (int j = nv_in < 0 ? 0 : nv_in; j < 4; ++j) {
-            sp->vrtx[j][0] = W.vx[j]; sp->vrtx[j][1] = W.vy[j]; sp->vrtx[j][2] = W.vz[j];
-            sp->vrtx_idx[j][0] = W.src1[j]; sp->vrtx_idx[j][1] = W.src2[j];
-          }
-        }
-        if (reported) {  // EPA.c:636-651
-          const uint32_t word = W.fv[report_face];
-          const int a = word & 0xff, b = (word >> 8) & 0xff, c = (word >> 16) & 0xff;
-          T a0, a1, a2;
-          origin_barycentric(work_vertex(W, a), work_vertex(W, b), work_vertex(W, c), a0, a1, a2);
-          const V3<T> pa = load3(A.c, W.src1[a]), pb = load3(A.c, W.src1[b]), pc = load3(A.c, W.src1[c]);
-          const V3<T> qa = load3(B.c, W.src2[a]), qb = load3(B.c, W.src2[b]), qc = load3(B.c, W.src2[c]);
-          sp->witnesses[0][0] = add_rn(add_rn(mul_rn(pa.x, a0), mul_rn(pb.x, a1)), mul_rn(pc.x, a2));
-          sp->witnesses[0][1] = add_rn(add_rn(mul_rn(pa.y, a0), mul_rn(pb.y, a1)), mul_rn(pc.y, a2));
-          sp->witnesses[0][2] = add_rn(add_rn(mul_rn(pa.z, a0), mul_rn(pb.z, a1)), mul_rn(pc.z, a2));
-          sp->witnesses[1][0] = add_rn(add_rn(mul_rn(qa.x, a0), mul_rn(qb.x, a1)), mul_rn(qc.x, a2));
-          sp->witnesses[1][1] = add_rn(add_rn(mul_rn(qa.y, a0), mul_rn(qb.y, a1)), mul_rn(qc.y, a2));
-          sp->witnesses[1][2] = add_rn(add_rn(mul_rn(qa.z, a0), mul_rn(qb.z, a1)), mul_rn(qc.z, a2));
-          nrm_out[0] = W.nx[report_face];
-          nrm_out[1] = W.ny[report_face];
-          nrm_out[2] = W.nz[report_face];
-          distances[pair] = -report_d;
-        }
-      }
-      phase = kIdle;
-    }
   }
 }
 

@@ -547,7 +547,17 @@ int launch_epa_group(const Source& src, int n, SimplexT<T>* d_simplices, T* d_di
   if (grid > need) grid = need;
   const bool sync_saved = t_sync;
   if (WT::kSmall) t_sync = false;  // the overflow pass follows
-  kern<<<(unsigned)grid, threads, smem, t_stream>>>(src, d_simplices, d_distances, d_normals, q.queue, q.counters, q.overflow);
+  // service batching of the group kernel (epa_group.cuh): development override OGJK_EPA_SVC=<batch><defer>, e.g. 23
+  int svc_batch = 2, svc_defer = 4;
+  if (const char* e = getenv("OGJK_EPA_SVC")) {
+    const int v = atoi(e);
+    svc_batch = v / 10 > 0 ? v / 10 : 1;
+    svc_defer = v % 10;
+  }
+  int hz_compact = 1;  // two-pass horizon (faces built from the compacted horizon list); OGJK_EPA_HZ=0 restores the one-pass form
+  if (const char* e = getenv("OGJK_EPA_HZ")) hz_compact = atoi(e);
+  kern<<<(unsigned)grid, threads, smem, t_stream>>>(src, d_simplices, d_distances, d_normals, q.queue, q.counters, q.overflow,
+                                                    svc_batch, svc_defer, hz_compact);
   int rc = finish_launch("epa group kernel");
   t_sync = sync_saved;
   if (rc || !WT::kSmall) return rc;
