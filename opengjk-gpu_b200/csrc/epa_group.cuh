@@ -16,7 +16,7 @@
 //   * reductions are 3-level xor butterflies on (value, lowest index);
 //   * face slot f belongs to lane f % G of the group; per-face passes run over the live slot range only;
 //   * both bodies' vertices are cached in registers (<= 64 per body: 8 per lane).
-// One warp per CTA.
+// WPC warps per CTA (independent of one another: no CTA-level synchronisation).
 //
 // Work area.  With the full-size EpaWork (4.7 KB, room for the reference's 64 iterations / 128 faces) only ~11 warps
 // fit an SM and the kernel is latency-bound (profiles/r1e_experiments.txt).  The measured distribution of EPA
@@ -37,16 +37,44 @@ namespace ogjk {
 template <typename T>
 struct EpaWorkSmall {
   using real = T;
-  static constexpr int kVerts = 28, kFaces = 56, kEdges = 48;
+  static constexpr int kVerts = 28, kFaces = 56, kEdges = 48, kRanks = 48;
+  static constexpr int kMaxBodyVerts = 65535;  // provenance is kept in 16 bits
   static constexpr bool kSmall = true;
   T vx[kVerts], vy[kVerts], vz[kVerts];
-  uint16_t src1[kVerts], src2[kVerts];  // bodies of up to 65 535 vertices (the launcher checks)
+  uint16_t src1[kVerts], src2[kVerts];
   T nx[kFaces], ny[kFaces], nz[kFaces];
   T fd[kFaces];
   uint32_t fv[kFaces];
   uint16_t edge[kEdges];
-  uint8_t rank2slot[kEdges];  // only the first `number of horizon edges` ranks are ever looked up
+  uint8_t rank2slot[kRanks];  // free slots below `hi`, lowest first
 };
+
+// The same with everything cut to what 99 % of the pairs need (config 3: 0.8 % of the pairs run more than 23 iterations,
+// configs 2 and 5: 0.3 % / 0.1 %): 26 vertices (22 expansions), 48 face slots, 12 dying faces per expansion, 16 free
+// slots below `hi`, 8-bit provenance -- 1424 bytes (fp32), so that 20 warps fit an SM (five 4-warp CTAs at 96
+// registers) where the 1.7 KB area allows 16.  Measured (profiles/r2y3_ab_epa_svc.txt): with bodies of up to 16 vertices
+// (KV = 4: 96 registers without spills) 3.86 -> 3.43 ms per Mi pairs; with 32-vertex bodies (KV = 8 wants 120 registers:
+// at 96 ptxas spills and the kernel is 20 % SLOWER -- 6.11 against 5.08 ms on config 3 -- while the area by itself costs
+// nothing, 5.13 ms at 128 registers), so only the KV = 4 instantiation uses it.
+// Bank layout: the eight groups of a warp read the same field of their own area in one instruction, four consecutive
+// words per group, so the areas start 4 * odd banks apart (356 words = 4 mod 32; EpaWorkSmall: 428 = 12 mod 32).
+template <typename T>
+struct EpaWorkTiny {
+  using real = T;
+  static constexpr int kVerts = 26, kFaces = 48, kEdges = 36, kRanks = 16;
+  static constexpr int kMaxBodyVerts = 255;  // provenance is kept in 8 bits
+  static constexpr bool kSmall = true;
+  T vx[kVerts], vy[kVerts], vz[kVerts];
+  T nx[kFaces], ny[kFaces], nz[kFaces];
+  T fd[kFaces];
+  uint32_t fv[kFaces];
+  alignas(8) uint16_t edge[kEdges];
+  uint8_t src1[kVerts], src2[kVerts];
+  uint8_t rank2slot[kRanks];
+  uint8_t pad[sizeof(T) == 4 ? 12 : 4];
+};
+static_assert(sizeof(EpaWorkTiny<float>) == 1424 && (sizeof(EpaWorkTiny<float>) / 4) % 32 == 4, "bank layout");
+static_assert((sizeof(EpaWorkSmall<float>) / 4) % 8 == 4, "bank layout");
 
 template <int G>
 struct Grp {
@@ -180,20 +208,15 @@ OGJK_D int grp_closest_face(const Grp<G>& g, const WT& W, int nj, int trips, T& 
   return bf == 0x7fffffff ? -1 : bf;
 }
 
-template <typename T>
-struct EpaGroupConfig {
-  static constexpr int kGroup = 8;
-  static constexpr int kThreads = 32;  // one warp per CTA: kThreads / kGroup work areas
-};
-
 // KV: vertices per lane of each body cached in registers (bodies of up to G * KV vertices; larger ones are read from
 // global memory on every support search).  WT: work area type (EpaWork<T> or EpaWorkSmall<T>).  counters: [0] queued
-// pairs, [1] ticket, [2] overflow count (small work area only: pairs appended to `overflow`).
-template <typename T, int G, int KV, typename WT, int MINB, typename Source>
-__global__ void __launch_bounds__(EpaGroupConfig<T>::kThreads, MINB)
+// pairs, [1] ticket, [2] overflow count (small work area only: pairs appended to `overflow`).  MINB: resident warps per SM
+// the registers are budgeted for (the launch bound is MINB / WPC CTAs of WPC warps).
+template <typename T, int G, int KV, typename WT, int MINB, int WPC, typename Source>
+__global__ void __launch_bounds__(32 * WPC, MINB / WPC)
 epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
                  T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters,
-                 int* __restrict__ overflow, int svc_batch, int svc_defer, int hz_compact) {
+                 int* __restrict__ overflow, int svc_batch, int svc_defer) {
   extern __shared__ __align__(16) unsigned char epa_smem[];
   WT* work = reinterpret_cast<WT*>(epa_smem);
   const int wlane = threadIdx.x & 31;
@@ -279,7 +302,7 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         cache_grp_verts<T, G, KV>(A, g.lane, LA);
         cache_grp_verts<T, G, KV>(B, g.lane, LB);
         g.sync();  // the previous pair's last reads of the work area are done
-        const bool oversize = WT::kSmall && (A.n > 65535 || B.n > 65535);  // provenance is kept in 16 bits
+        const bool oversize = WT::kSmall && (A.n > WT::kMaxBodyVerts || B.n > WT::kMaxBodyVerts);
         if (oversize && g.lane == 0) overflow[atomicAdd(&counters[2], 1)] = (int)pair;  // phase stays kIdle
         nv_in = sp->nvrtx;
         nv = nv_in;
@@ -530,12 +553,12 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         }
         if (free_now) {
           const int r = nfree_lo + __popc(fm & g.below());
-          if (!WT::kSmall || r < WT::kEdges) W.rank2slot[r] = (uint8_t)f;
+          if (!WT::kSmall || r < WT::kRanks) W.rank2slot[r] = (uint8_t)f;
         }
         nvis += __popc(vm);
         nfree_lo += __popc(fm);
       }
-      if (WT::kSmall && act && 3 * nvis > WT::kEdges) {  // more dying faces than the edge list holds
+      if (WT::kSmall && act && (3 * nvis > WT::kEdges || nfree_lo > WT::kRanks)) {  // more dying faces than the lists hold
         ovf = true;
         act = false;
         nvis = 0;
@@ -585,23 +608,15 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
           const int q2 = base_rank + __popc(keepm & g.below());
           if (q2 < nfree) {
             const int slot = free_slot(q2);
-            if (hz_compact) {
-              W.fv[slot] = key;  // parked in its (free: live byte 0) slot until the face pass below
-            } else {
-              const int lo = (int)(key & 0xffu), hi8 = (int)((key >> 8) & 0x7fu);
-              const bool rev = (key & 0x8000u) != 0u;
-              bool degenerate = false;
-              const uint32_t word = make_face(W, slot, rev ? hi8 : lo, rev ? lo : hi8, newv, centroid, degenerate);
-              W.fv[slot] = word;
-              if (degenerate) any_degenerate = true;
-            }
+            W.fv[slot] = key;  // parked in its (free: live byte 0) slot until the face pass below
           }
         }
         base_rank += __popc(keepm);
       }
-      if (hz_compact) {
-        // The horizon edges are now parked one per new slot, in rank order: build the faces in a second pass whose trip
-        // count is the number of NEW faces (dying faces + 2) instead of the number of dying-face edges (3 per face).
+      {
+        // The horizon edges are now parked one per new slot, in rank order: the faces are built in a second pass whose
+        // trip count is the number of NEW faces (dying faces + 2) instead of the number of dying-face edges (3 per face)
+        // -- measured: config 3 5.49 -> 5.41 ms per Mi pairs (profiles/r2x_ab_epa_svc.txt).
         const int used_now = base_rank < nfree ? base_rank : nfree;
         const int usedw = __reduce_max_sync(0xffffffffu, used_now);
         __syncwarp();

@@ -534,13 +534,13 @@ int launch_epa_warp_queue(const Source& src, int n, SimplexT<T>* d_simplices, T*
   return finish_launch("epa kernel");
 }
 
-template <typename T, int G, int KV, typename WT, int MINB, typename Source>
+template <typename T, int G, int KV, typename WT, int MINB, int WPC, typename Source>
 int launch_epa_group(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distances, T* d_normals, const EpaQueue& q,
                      int sms) {
-  constexpr int threads = EpaGroupConfig<T>::kThreads;
+  constexpr int threads = 32 * WPC;
   constexpr int groups = threads / G;
   const size_t smem = (size_t)groups * sizeof(WT);
-  auto kern = epa_group_kernel<T, G, KV, WT, MINB, Source>;
+  auto kern = epa_group_kernel<T, G, KV, WT, MINB, WPC, Source>;
   long long grid = 0;
   if (int rc = persistent_grid(kern, threads, smem, &grid)) return rc;
   const long long need = ((long long)n + groups - 1) / groups;
@@ -554,10 +554,8 @@ int launch_epa_group(const Source& src, int n, SimplexT<T>* d_simplices, T* d_di
     svc_batch = v / 10 > 0 ? v / 10 : 1;
     svc_defer = v % 10;
   }
-  int hz_compact = 1;  // two-pass horizon (faces built from the compacted horizon list); OGJK_EPA_HZ=0 restores the one-pass form
-  if (const char* e = getenv("OGJK_EPA_HZ")) hz_compact = atoi(e);
   kern<<<(unsigned)grid, threads, smem, t_stream>>>(src, d_simplices, d_distances, d_normals, q.queue, q.counters, q.overflow,
-                                                    svc_batch, svc_defer, hz_compact);
+                                                    svc_batch, svc_defer);
   int rc = finish_launch("epa group kernel");
   t_sync = sync_saved;
   if (rc || !WT::kSmall) return rc;
@@ -582,13 +580,28 @@ int launch_epa_queue(const Source& src, int n, int nv_hint, SimplexT<T>* d_simpl
   int mode = nv_hint <= 32 ? 4 : 0;  // 0 warp per pair, 4 / 8 small work area with that many lanes, 1 full-size group
   if (e) mode = !strcmp(e, "warp") ? 0 : !strcmp(e, "group") ? 1 : !strcmp(e, "small4") ? 4 : !strcmp(e, "small8") ? 8 : mode;
   constexpr int minb = sizeof(T) == 4 ? 16 : 8;
-  if (mode == 4) {
-    if (nv_hint <= 16)
-      return launch_epa_group<T, 4, 4, EpaWorkSmall<T>, minb, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
-    return launch_epa_group<T, 4, 8, EpaWorkSmall<T>, minb, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
+  if constexpr (sizeof(T) == 4) {  // experiment: 8 lanes x 4 vertices with the 1.4 KB area at 20 / 24 warps per SM
+    if (e && !strcmp(e, "tiny8a") && nv_hint <= 32)
+      return launch_epa_group<T, 8, 4, EpaWorkTiny<T>, 20, 4, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
+    if (e && !strcmp(e, "tiny8b") && nv_hint <= 32)
+      return launch_epa_group<T, 8, 4, EpaWorkTiny<T>, 24, 4, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
   }
-  if (mode == 8) return launch_epa_group<T, 8, 8, EpaWorkSmall<T>, minb, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
-  if (mode == 1) return launch_epa_group<T, 8, 8, EpaWork<T>, 1, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
+  if (mode == 4) {
+    // Two warps per CTA: eight 2-warp CTAs use the 1 KB of shared memory the system reserves per CTA eight times instead
+    // of fifteen times -- 16 warps per SM instead of 15 (config 3: 5.31 -> 5.07 ms, profiles/r2y_ab_epa_svc.txt).
+    // Bodies of up to 16 vertices (KV = 4 needs 96 registers) take the 1.4 KB area: 20 warps per SM, 3.86 -> 3.43 ms.
+    if (nv_hint <= 16) {
+      const char* area = getenv("OGJK_EPA_AREA");  // development: small | tiny
+      if constexpr (sizeof(T) == 4) {
+        if (!area || strcmp(area, "small"))
+          return launch_epa_group<T, 4, 4, EpaWorkTiny<T>, 20, 4, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
+      }
+      return launch_epa_group<T, 4, 4, EpaWorkSmall<T>, minb, 2, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
+    }
+    return launch_epa_group<T, 4, 8, EpaWorkSmall<T>, minb, 2, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
+  }
+  if (mode == 8) return launch_epa_group<T, 8, 8, EpaWorkSmall<T>, minb, 1, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
+  if (mode == 1) return launch_epa_group<T, 8, 8, EpaWork<T>, 1, 1, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
   return launch_epa_warp_queue<T, Source>(src, n, d_simplices, d_distances, d_normals, q.queue, q.counters, sms);
 }
 

@@ -1,5 +1,5 @@
-"""A/B of the EPA group kernel's service batching (OGJK_EPA_SVC=<batch><defer>) and two-pass horizon (OGJK_EPA_HZ=0|1) on
-configs 3 and 5, 16-vertex bodies and (G = 8, OGJK_EPA_KERNEL=small8) config 2.  Variants: <svc>:<hz>[:<kernel>]."""
+"""A/B of the EPA group kernel's service batching (OGJK_EPA_SVC=<batch><defer>) and warps per CTA (OGJK_EPA_WPC=1|2|4) on
+configs 3 and 5, 16-vertex bodies and config 2.  Variants: <svc>:<wpc>[:<area>]  (area = OGJK_EPA_AREA: small | tiny)."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,13 +7,13 @@ from _pkgpath import load_package
 pkg = load_package()
 eng = pkg.Engine(np.float32); eng.set_device(0); eng.set_sync(False)
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
-variants = sys.argv[1:] or ["10:0", "24:0", "24:1", "33:1", "23:1"]
+variants = sys.argv[1:] or ["24:1", "24:2", "24:4", "34:2", "25:2"]
 def run(tag, step, n):
     for v in variants:
         f = v.split(":")
         os.environ["OGJK_EPA_SVC"] = f[0]
-        os.environ["OGJK_EPA_HZ"] = f[1] if len(f) > 1 else "0"
-        if len(f) > 2: os.environ["OGJK_EPA_KERNEL"] = f[2]
+        os.environ["OGJK_EPA_WPC"] = f[1] if len(f) > 1 else "1"
+        if len(f) > 2 and f[2].startswith("tiny8"): os.environ["OGJK_EPA_KERNEL"] = f[2]
         else: os.environ.pop("OGJK_EPA_KERNEL", None)
         for _ in range(2): step()
         torch.cuda.synchronize()
@@ -22,7 +22,7 @@ def run(tag, step, n):
         torch.cuda.synchronize()
         g, e, c = eng.stage_times(); eng.set_timing(False)
         print(f"{tag} svc={v}: gjk {g/c:.3f} ms  epa {e/c:.3f} ms", flush=True)
-    for k in ("OGJK_EPA_SVC", "OGJK_EPA_HZ", "OGJK_EPA_KERNEL"): os.environ.pop(k, None)
+    for k in ("OGJK_EPA_SVC", "OGJK_EPA_WPC", "OGJK_EPA_KERNEL"): os.environ.pop(k, None)
 for name, n, nv, spread in (("cfg3 1Mi x32 S=1", 1 << 20, 32, 1.0), ("small 1Mi x16 S=0.5", 1 << 20, 16, 0.5), ("cfg2 1Mi x64 S=10", 1 << 20, 64, 10.0)):
     a, b = pkg.workloads.random_pairs(n, nv, spread, seed=12345, dtype=np.float32)
     da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
