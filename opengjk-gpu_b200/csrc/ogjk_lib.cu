@@ -563,13 +563,15 @@ int launch_epa_group(const Source& src, int n, SimplexT<T>* d_simplices, T* d_di
   return launch_epa_warp_queue<T, Source>(src, n, d_simplices, d_distances, d_normals, q.overflow, q.counters + 2, sms);
 }
 
-// Persistent EPA over a device-side queue of colliding pairs.  Default (measured on B200, profiles/r2q_ab_epa.txt):
-// bodies of up to 32 vertices take the sub-warp group kernel with the small work area, G = 4 lanes per pair, followed
-// by the overflow pass -- config 3: 5.88 ms against 7.64 ms per Mi pairs for one warp per pair, config 5: 10.6
-// against 14.1 ms per 4 M pairs, 16-vertex bodies 4.34 against 6.43; larger bodies (the support scan grows, the
-// bookkeeping does not) take one warp per pair -- config 2 (64 vertices, shallow contacts): 0.29 ms against 0.33 (G = 8)
-// and 0.48 (G = 4); only deep 64-vertex contacts favour G = 8 (3.04 against 3.42 ms per 512 Ki pairs).  Development
-// overrides: OGJK_EPA_KERNEL=warp|group (group = full-size work area, 8 lanes)|small4|small8.
+// Persistent EPA over a device-side queue of colliding pairs.  Default (measured on B200, profiles/r2_experiments.txt
+// sections A, E, G): bodies of up to 32 vertices take the sub-warp group kernel, G = 4 lanes per pair, followed by the
+// overflow pass -- config 3: 5.07 ms against 7.64 ms per Mi pairs for one warp per pair, config 5: 8.85 against 14.1 ms
+// per 3.96 M pairs, 16-vertex bodies 3.43 against 6.43; larger bodies (the support scan grows, the bookkeeping does
+// not) take one warp per pair -- config 2 (64 vertices, shallow contacts): 0.30 ms against 0.34 (G = 8) and 0.48
+// (G = 4); only deep 64-vertex contacts favour G = 8 (3.04 against 3.42 ms per 512 Ki pairs).  Measured and dropped
+// (profiles/r2y5_ab_epa_svc.txt): G = 8 with four cached vertices per lane and the 1.4 KB area at 20 / 24 warps per SM
+// -- config 3 5.50 / 5.48 ms.  Development overrides: OGJK_EPA_KERNEL=warp|group (full-size area, 8 lanes)|small4|small8,
+// OGJK_EPA_SVC=<batch><defer>, OGJK_EPA_AREA=small (bodies of up to 16 vertices: 1.7 KB area instead of 1.4 KB).
 template <typename T, typename Source>
 int launch_epa_queue(const Source& src, int n, int nv_hint, SimplexT<T>* d_simplices, T* d_distances, T* d_normals,
                      const EpaQueue& q) {
@@ -580,12 +582,6 @@ int launch_epa_queue(const Source& src, int n, int nv_hint, SimplexT<T>* d_simpl
   int mode = nv_hint <= 32 ? 4 : 0;  // 0 warp per pair, 4 / 8 small work area with that many lanes, 1 full-size group
   if (e) mode = !strcmp(e, "warp") ? 0 : !strcmp(e, "group") ? 1 : !strcmp(e, "small4") ? 4 : !strcmp(e, "small8") ? 8 : mode;
   constexpr int minb = sizeof(T) == 4 ? 16 : 8;
-  if constexpr (sizeof(T) == 4) {  // experiment: 8 lanes x 4 vertices with the 1.4 KB area at 20 / 24 warps per SM
-    if (e && !strcmp(e, "tiny8a") && nv_hint <= 32)
-      return launch_epa_group<T, 8, 4, EpaWorkTiny<T>, 20, 4, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
-    if (e && !strcmp(e, "tiny8b") && nv_hint <= 32)
-      return launch_epa_group<T, 8, 4, EpaWorkTiny<T>, 24, 4, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
-  }
   if (mode == 4) {
     // Two warps per CTA: eight 2-warp CTAs use the 1 KB of shared memory the system reserves per CTA eight times instead
     // of fifteen times -- 16 warps per SM instead of 15 (config 3: 5.31 -> 5.07 ms, profiles/r2y_ab_epa_svc.txt).

@@ -1,5 +1,7 @@
-"""A/B of the EPA group kernel's service batching (OGJK_EPA_SVC=<batch><defer>) and warps per CTA (OGJK_EPA_WPC=1|2|4) on
-configs 3 and 5, 16-vertex bodies and config 2.  Variants: <svc>:<wpc>[:<area>]  (area = OGJK_EPA_AREA: small | tiny)."""
+"""A/B of the EPA group kernel's service batching (OGJK_EPA_SVC=<batch><defer>) and work area for bodies of up to 16
+vertices (OGJK_EPA_AREA=small|tiny) on configs 3 and 5, 16-vertex bodies and config 2.  Variants: <svc>[:<area>].
+(The warps-per-CTA, horizon and 8-lane variants timed with earlier versions of this script -- profiles/r2x_*, r2y*_ab_epa_svc.txt
+-- were compile-time instantiations that have since been removed.)"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,14 +9,13 @@ from _pkgpath import load_package
 pkg = load_package()
 eng = pkg.Engine(np.float32); eng.set_device(0); eng.set_sync(False)
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
-variants = sys.argv[1:] or ["24:1", "24:2", "24:4", "34:2", "25:2"]
+variants = sys.argv[1:] or ["10", "24", "34", "24:small"]
 def run(tag, step, n):
     for v in variants:
         f = v.split(":")
         os.environ["OGJK_EPA_SVC"] = f[0]
-        os.environ["OGJK_EPA_WPC"] = f[1] if len(f) > 1 else "1"
-        if len(f) > 2 and f[2].startswith("tiny8"): os.environ["OGJK_EPA_KERNEL"] = f[2]
-        else: os.environ.pop("OGJK_EPA_KERNEL", None)
+        if len(f) > 1: os.environ["OGJK_EPA_AREA"] = f[1]
+        else: os.environ.pop("OGJK_EPA_AREA", None)
         for _ in range(2): step()
         torch.cuda.synchronize()
         eng.set_timing(True)
@@ -22,7 +23,7 @@ def run(tag, step, n):
         torch.cuda.synchronize()
         g, e, c = eng.stage_times(); eng.set_timing(False)
         print(f"{tag} svc={v}: gjk {g/c:.3f} ms  epa {e/c:.3f} ms", flush=True)
-    for k in ("OGJK_EPA_SVC", "OGJK_EPA_WPC", "OGJK_EPA_KERNEL"): os.environ.pop(k, None)
+    for k in ("OGJK_EPA_SVC", "OGJK_EPA_AREA"): os.environ.pop(k, None)
 for name, n, nv, spread in (("cfg3 1Mi x32 S=1", 1 << 20, 32, 1.0), ("small 1Mi x16 S=0.5", 1 << 20, 16, 0.5), ("cfg2 1Mi x64 S=10", 1 << 20, 64, 10.0)):
     a, b = pkg.workloads.random_pairs(n, nv, spread, seed=12345, dtype=np.float32)
     da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
