@@ -39,7 +39,7 @@ struct EpaWorkSmall {
   using real = T;
   static constexpr int kVerts = 28, kFaces = 56, kEdges = 48, kRanks = 48;
   static constexpr int kMaxBodyVerts = 65535;  // provenance is kept in 16 bits
-  static constexpr bool kSmall = true;
+  static constexpr bool kSmall = true, kLean = false;
   T vx[kVerts], vy[kVerts], vz[kVerts];
   uint16_t src1[kVerts], src2[kVerts];
   T nx[kFaces], ny[kFaces], nz[kFaces];
@@ -63,7 +63,7 @@ struct EpaWorkTiny {
   using real = T;
   static constexpr int kVerts = 26, kFaces = 48, kEdges = 36, kRanks = 16;
   static constexpr int kMaxBodyVerts = 255;  // provenance is kept in 8 bits
-  static constexpr bool kSmall = true;
+  static constexpr bool kSmall = true, kLean = false;
   T vx[kVerts], vy[kVerts], vz[kVerts];
   T nx[kFaces], ny[kFaces], nz[kFaces];
   T fd[kFaces];
@@ -75,6 +75,42 @@ struct EpaWorkTiny {
 };
 static_assert(sizeof(EpaWorkTiny<float>) == 1424 && (sizeof(EpaWorkTiny<float>) / 4) % 32 == 4, "bank layout");
 static_assert((sizeof(EpaWorkSmall<float>) / 4) % 8 == 4, "bank layout");
+
+// The LEAN area: EpaWorkTiny (one vertex less) plus the per-pair state that the kernel otherwise carries in registers
+// across the expansion loop -- running centroid, the two body pointers, the report record, the pair index, and `nv` / `hi`,
+// which are parked here while the support search has all 48 cached coordinates live.  Together with the bodies' vertex
+// counts folded into a per-lane count of cached vertices (bodies that are not fully cached go to the overflow queue) and
+// the iteration counter dropped (it is nv - 4), the 32-vertex instantiation (KV = 8) comes down from 120 to 96 registers
+// with one to three local-memory loads per expansion step: five 4-warp CTAs = 20 warps per SM instead of 16.
+// (Spills are poison here: shared memory takes nearly all of L1, so a local load is an L2 round trip on the warp's
+// critical path -- the first 96-register build, ~30 spill instructions per step, was 20 % slower than the 128-register
+// one, profiles/r2y3_ab_epa_svc.txt.  And nothing between 128 and 96 registers helps: a scheduler owns 16 K registers,
+// i.e. 4 warps at 97..128 registers per thread and 5 at 96 -- two 9-warp CTAs at 112 registers ran ONE CTA per SM, 7.81 ms,
+// and a 19-warp CTA at 104 did not launch, profiles/r2y6_ab_epa_svc.txt.)
+// Measured (profiles/r2y7_ab_epa_svc.txt): config 3 5.09 -> 4.88 ms per Mi pairs, config 5 8.89 -> 8.40 ms per 3.96 M pairs;
+// the same area at 128 registers / 16 warps costs 2 % (5.20 / 9.12: the smaller area's overflow and the parked state).
+template <typename T>
+struct EpaWorkLean {
+  using real = T;
+  static constexpr int kVerts = 25, kFaces = 46, kEdges = 36, kRanks = 12;
+  static constexpr int kMaxBodyVerts = 255;
+  static constexpr bool kSmall = true, kLean = true;
+  T vx[kVerts], vy[kVerts], vz[kVerts];
+  T nx[kFaces], ny[kFaces], nz[kFaces];
+  T fd[kFaces];
+  uint32_t fv[kFaces];
+  alignas(8) uint16_t edge[kEdges];
+  const T* body1;  // coordinates of the pair's two bodies
+  const T* body2;
+  T cx, cy, cz;    // running centroid
+  uint8_t src1[kVerts], src2[kVerts];
+  uint8_t rank2slot[kRanks];
+  int8_t report_face;  // -1: nothing to report (the reported distance is fd[report_face])
+  int8_t nv_in;
+  uint8_t nv, hi;  // parked here while the support search has all 48 cached coordinates live
+  int pair;
+};
+static_assert(sizeof(EpaWorkLean<float>) <= 1424, "five 4-warp CTAs per SM: (32 areas + 1 KB) x 5 <= 228 KB");
 
 template <int G>
 struct Grp {
@@ -169,6 +205,22 @@ OGJK_D void grp_lane_support(const BodyRef<T>& A, const GrpVerts<T, G, KV>& L, c
     }
   }
 }
+// the same for a body that is known to be cached; `cnt` = how many of this lane's KV slots hold a vertex
+template <typename T, int G, int KV>
+OGJK_D void grp_lane_support_cached(const GrpVerts<T, G, KV>& L, int cnt, const V3<T>& d, bool negate, int glane, T& best,
+                                    int& bi) {
+  best = (T)-1e10f;
+  bi = 0x7fffffff;
+#pragma unroll
+  for (int k = 0; k < KV; ++k) {
+    T sv = dot(L.p[k].x, L.p[k].y, L.p[k].z, d);
+    if (negate) sv = -sv;
+    if (k < cnt && sv > best) {
+      best = sv;
+      bi = glane + G * k;
+    }
+  }
+}
 // EPA.c:307-344 (see epa_support)
 template <typename T, int G, int KV>
 OGJK_D bool grp_support(const Grp<G>& g, const BodyRef<T>& A, const BodyRef<T>& B, const GrpVerts<T, G, KV>& LA,
@@ -212,32 +264,32 @@ OGJK_D int grp_closest_face(const Grp<G>& g, const WT& W, int nj, int trips, T& 
 // global memory on every support search).  WT: work area type (EpaWork<T> or EpaWorkSmall<T>).  counters: [0] queued
 // pairs, [1] ticket, [2] overflow count (small work area only: pairs appended to `overflow`).  MINB: resident warps per SM
 // the registers are budgeted for (the launch bound is MINB / WPC CTAs of WPC warps).
-template <typename T, int G, int KV, typename WT, int MINB, int WPC, typename Source>
-__global__ void __launch_bounds__(32 * WPC, MINB / WPC)
-epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
-                 T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters,
-                 int* __restrict__ overflow, int svc_batch, int svc_defer) {
+template <typename T, int G, int KV, typename WT, typename Source>
+OGJK_D void epa_group_body(const Source& src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
+                           T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters,
+                           int* __restrict__ overflow, int svc_batch, int svc_defer) {
   extern __shared__ __align__(16) unsigned char epa_smem[];
   WT* work = reinterpret_cast<WT*>(epa_smem);
   const int wlane = threadIdx.x & 31;
   const Grp<G> g(wlane);
   WT& W = work[threadIdx.x / G];
-  const int count = counters[0];
   const T eps = Tol<T>::eps();
   const T tol = Tol<T>::eps_tot();
 
   enum { kIdle = 0, kExpand = 1, kReport = 2, kExit = 3 };
   int phase = kIdle;
   // per-pair state, replicated on the lanes of the group
-  long long pair = 0;
-  SimplexT<T>* sp = nullptr;
+  constexpr bool kLean = WT::kLean;
+  int pair = 0;  // (the queue holds ints)
+  SimplexT<T>* sp = nullptr;  // (lean: recomputed from `pair` where needed)
   T* nrm_out = nullptr;
-  BodyRef<T> A, B;
+  BodyRef<T> A, B;  // (lean: only alive during set-up; the loop uses the cached vertices, the report W.body1/2)
   A.c = B.c = nullptr;
   A.n = B.n = 0;
   GrpVerts<T, G, KV> LA, LB;
   LA.cached = LB.cached = false;
-  int nv_in = 0, nv = 0, iter = 0, hi = 4;
+  unsigned vcnt = 0;  // lean: number of cached vertices of this lane, body 1 | body 2 << 8
+  int nv_in = 0, nv = 0, hi = 4;  // (the iteration count of an expanding pair is nv - 4: every step but the last adds a vertex)
   V3<T> centroid = mk<T>(T(0), T(0), T(0));
   bool reported = false;
   int report_face = -1;
@@ -258,6 +310,19 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
     }
     // ================================ outputs ======================================================================
     if (service && phase == kReport) {
+      if constexpr (kLean) {
+        pair = W.pair;
+        sp = simplices + pair;
+        nrm_out = normals + 3 * (size_t)pair;
+        if (g.lane == 0) {
+          nv_in = W.nv_in;
+          report_face = W.report_face;
+          reported = report_face >= 0;
+          report_d = reported ? W.fd[report_face] : T(0);
+          A.c = W.body1;
+          B.c = W.body2;
+        }
+      }
       if (g.lane == 0) {
         if (nv_in != 4) {  // the regrown simplex is part of the result (EPA.c modifies it in place)
           sp->nvrtx = 4;
@@ -292,7 +357,7 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
       int q = 0;
       if (g.lane == 0) q = atomicAdd(&counters[1], 1);
       q = g.bcast(q, 0);
-      if (q >= count) {
+      if (q >= *reinterpret_cast<const volatile int*>(&counters[0])) {  // (not kept in a register across the loop)
         phase = kExit;
       } else {
         pair = queue[q];
@@ -302,7 +367,12 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         cache_grp_verts<T, G, KV>(A, g.lane, LA);
         cache_grp_verts<T, G, KV>(B, g.lane, LB);
         g.sync();  // the previous pair's last reads of the work area are done
-        const bool oversize = WT::kSmall && (A.n > WT::kMaxBodyVerts || B.n > WT::kMaxBodyVerts);
+        bool oversize = WT::kSmall && (A.n > WT::kMaxBodyVerts || B.n > WT::kMaxBodyVerts);
+        if constexpr (kLean) {  // the lean loop only knows the cached vertices
+          oversize = oversize || A.n > G * KV || B.n > G * KV;
+          const int c1 = (A.n - g.lane + G - 1) / G, c2 = (B.n - g.lane + G - 1) / G;  // vertices lane, lane + G, ... < n
+          vcnt = (unsigned)(c1 < 0 ? 0 : (c1 > KV ? KV : c1)) | ((unsigned)(c2 < 0 ? 0 : (c2 > KV ? KV : c2)) << 8);
+        }
         if (oversize && g.lane == 0) overflow[atomicAdd(&counters[2], 1)] = (int)pair;  // phase stays kIdle
         nv_in = sp->nvrtx;
         nv = nv_in;
@@ -413,11 +483,23 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
             W.fv[l] = degenerate ? (word & 0x00ffffffu) : word;
           }
           g.sync();
-          iter = 0;
           hi = 4;
           reported = false;
           report_face = -1;
           report_d = T(0);
+          if constexpr (kLean) {
+            if (g.lane == 0) {
+              W.cx = centroid.x; W.cy = centroid.y; W.cz = centroid.z;
+              W.body1 = A.c;
+              W.body2 = B.c;
+              W.report_face = -1;
+              W.nv_in = (int8_t)nv_in;
+              W.nv = 4;
+              W.hi = 4;
+              W.pair = pair;
+            }
+            g.sync();
+          }
           phase = kExpand;
         }
       }
@@ -431,23 +513,29 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
     if (__any_sync(0xffffffffu, phase == kExpand)) {
       const Grp<G> gw(wlane, true);
       bool act = phase == kExpand;
-      if (__any_sync(0xffffffffu, act && iter >= kEpaMaxIters)) {  // iteration cap (EPA.c:828-863): rare
-        const bool cap = act && iter >= kEpaMaxIters;
+      if (WT::kVerts >= kEpaMaxVerts && __any_sync(0xffffffffu, act && nv - 4 >= kEpaMaxIters)) {  // iteration cap (EPA.c:828-863): rare;
+        const bool cap = act && nv - 4 >= kEpaMaxIters;  // an area with fewer vertices hands the pair over long before
         T cd;
         constexpr int kAllTrips = (WT::kFaces + G - 1) / G;
         const int cf = grp_closest_face<T, G, WT>(gw, W, cap ? kAllTrips : 0, kAllTrips, cd);
         if (cap) {
           if (cf >= 0) {
-            reported = true;
-            report_face = cf;
-            report_d = cd;
+            if constexpr (kLean) {
+              if (g.lane == 0) {
+                W.report_face = (int8_t)cf;
+              }
+            } else {
+              reported = true;
+              report_face = cf;
+              report_d = cd;
+            }
           }
           phase = kReport;
           act = false;
         }
       }
-      if (act) ++iter;
-      const int nj = act ? (hi + G - 1) / G : 0;
+      if constexpr (kLean) hi = W.hi;
+      int nj = act ? (hi + G - 1) / G : 0;
       const int njw = __reduce_max_sync(0xffffffffu, nj);
       T cd;
       int cf = grp_closest_face<T, G, WT>(gw, W, nj, njw, cd);
@@ -463,8 +551,13 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         T b1 = (T)-1e10f, b2 = (T)-1e10f;
         int k1 = 0x7fffffff, k2 = 0x7fffffff;
         if (act) {  // no collective inside; idle groups may hold stale body descriptors
-          grp_lane_support<T, G, KV>(A, LA, cn, false, g.lane, b1, k1);
-          grp_lane_support<T, G, KV>(B, LB, cn, true, g.lane, b2, k2);
+          if constexpr (kLean) {
+            grp_lane_support_cached<T, G, KV>(LA, (int)(vcnt & 0xffu), cn, false, g.lane, b1, k1);
+            grp_lane_support_cached<T, G, KV>(LB, (int)(vcnt >> 8), cn, true, g.lane, b2, k2);
+          } else {
+            grp_lane_support<T, G, KV>(A, LA, cn, false, g.lane, b1, k1);
+            grp_lane_support<T, G, KV>(B, LB, cn, true, g.lane, b2, k2);
+          }
         }
         grp_argmax<T, G>(gw, b1, k1);
         grp_argmax<T, G>(gw, b2, k2);
@@ -473,10 +566,18 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
           act = false;
         }
         if (act) {
-          w = vsub(load3(A.c, k1), load3(B.c, k2));
+          if constexpr (kLean) w = vsub(load3(W.body1, k1), load3(W.body2, k2));
+          else w = vsub(load3(A.c, k1), load3(B.c, k2));
           i1 = k1;
           i2 = k2;
         }
+      }
+      if constexpr (kLean) {  // nothing of the step's bookkeeping was kept in registers across the support search
+        asm volatile("" ::: "memory");
+        hi = W.hi;
+        nv = W.nv;
+        nj = act ? (hi + G - 1) / G : 0;
+        cd = W.fd[cf];  // (cf is 0 for idle groups)
       }
       bool stop = sub_rn(dot(cn, w), cd) < tol;
       {  // duplicate of an existing polytope vertex? (EPA.c:654-665)
@@ -492,9 +593,15 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         if (gw.any(dup)) stop = true;
       }
       if (act && stop) {
-        reported = true;
-        report_face = cf;
-        report_d = cd;
+        if constexpr (kLean) {
+          if (g.lane == 0) {
+            W.report_face = (int8_t)cf;
+          }
+        } else {
+          reported = true;
+          report_face = cf;
+          report_d = cd;
+        }
         phase = kReport;
         act = false;
       }
@@ -515,9 +622,19 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         }
         ++nv;
         const T inv_n = div_rn(T(1), (T)nv);
-        centroid.x = add_rn(centroid.x, mul_rn(sub_rn(w.x, centroid.x), inv_n));
-        centroid.y = add_rn(centroid.y, mul_rn(sub_rn(w.y, centroid.y), inv_n));
-        centroid.z = add_rn(centroid.z, mul_rn(sub_rn(w.z, centroid.z), inv_n));
+        if constexpr (kLean) {
+          if (g.lane == 0) {  // read by the face pass, behind the __syncwarp() in front of the horizon loop
+            W.nv = (uint8_t)nv;
+            const T ox = W.cx, oy = W.cy, oz = W.cz;
+            W.cx = add_rn(ox, mul_rn(sub_rn(w.x, ox), inv_n));
+            W.cy = add_rn(oy, mul_rn(sub_rn(w.y, oy), inv_n));
+            W.cz = add_rn(oz, mul_rn(sub_rn(w.z, oz), inv_n));
+          }
+        } else {
+          centroid.x = add_rn(centroid.x, mul_rn(sub_rn(w.x, centroid.x), inv_n));
+          centroid.y = add_rn(centroid.y, mul_rn(sub_rn(w.y, centroid.y), inv_n));
+          centroid.z = add_rn(centroid.z, mul_rn(sub_rn(w.z, centroid.z), inv_n));
+        }
       }
 
       // faces that see the new vertex die; their directed edges go to the scratch list in (slot, corner) order.  An edge
@@ -623,6 +740,7 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         for (int r0 = 0; r0 < usedw; r0 += G) {
           const int r = r0 + g.lane;
           if (r < used_now) {
+            if constexpr (kLean) centroid = mk<T>(W.cx, W.cy, W.cz);
             const int slot = free_slot(r);
             const uint32_t key = W.fv[slot];
             const int lo = (int)(key & 0xffu), hi8 = (int)((key >> 8) & 0x7fu);
@@ -640,6 +758,7 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
       }
       if (WT::kSmall && gw.any(ovf)) {  // (warp-uniform branch: every group looks at its own lanes' bits)
         if (ovf) {
+          if constexpr (kLean) pair = W.pair;
           if (g.lane == 0) overflow[atomicAdd(&counters[2], 1)] = (int)pair;
           phase = kIdle;
         }
@@ -649,6 +768,9 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
         if (used > 0) {
           const int top = free_slot(used - 1) + 1;  // ranks ascend with slots
           hi = top > hi ? top : hi;
+          if constexpr (kLean) {
+            if (g.lane == 0) W.hi = (uint8_t)hi;
+          }
         }
       }
       __syncwarp();
@@ -664,6 +786,24 @@ epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __res
     }
 
   }
+}
+
+// The register budget is given either as resident warps per SM (MINB: launch bound of MINB / WPC CTAs of WPC warps) ...
+template <typename T, int G, int KV, typename WT, int MINB, int WPC, typename Source>
+__global__ void __launch_bounds__(32 * WPC, MINB / WPC)
+epa_group_kernel(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
+                 T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters,
+                 int* __restrict__ overflow, int svc_batch, int svc_defer) {
+  epa_group_body<T, G, KV, WT, Source>(src, simplices, distances, normals, queue, counters, overflow, svc_batch, svc_defer);
+}
+// ... or as registers per thread (with a minimum-CTA launch bound ptxas settles on 96 registers for anything between 17
+// and 20 warps per SM; the lean instantiation needs exactly 104 to stay free of spills).
+template <typename T, int G, int KV, typename WT, int REGS, int WPC, typename Source>
+__global__ void __launch_bounds__(32 * WPC) __maxnreg__(REGS)
+epa_group_kernel_regs(const Source src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
+                      T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters,
+                      int* __restrict__ overflow, int svc_batch, int svc_defer) {
+  epa_group_body<T, G, KV, WT, Source>(src, simplices, distances, normals, queue, counters, overflow, svc_batch, svc_defer);
 }
 
 }  // namespace ogjk

@@ -42,7 +42,7 @@ struct EpaWork {
   using real = T;
   static constexpr int kVerts = kEpaMaxVerts, kFaces = kEpaMaxFaces, kEdges = kEpaMaxFaces * 3, kRanks = kEpaMaxFaces;
   static constexpr int kMaxBodyVerts = 0x7fffffff;
-  static constexpr bool kSmall = false;
+  static constexpr bool kSmall = false, kLean = false;
   T vx[kEpaMaxVerts], vy[kEpaMaxVerts], vz[kEpaMaxVerts];  // Minkowski-difference vertices
   int src1[kEpaMaxVerts], src2[kEpaMaxVerts];              // provenance: vertex index on body 1 / body 2
   T nx[kEpaMaxFaces], ny[kEpaMaxFaces], nz[kEpaMaxFaces];  // unit outward normals

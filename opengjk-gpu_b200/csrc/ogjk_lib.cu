@@ -534,13 +534,16 @@ int launch_epa_warp_queue(const Source& src, int n, SimplexT<T>* d_simplices, T*
   return finish_launch("epa kernel");
 }
 
-template <typename T, int G, int KV, typename WT, int MINB, int WPC, typename Source>
+// BYREGS: the register budget MINB is registers per thread (epa_group_kernel_regs) instead of resident warps per SM
+template <typename T, int G, int KV, typename WT, int MINB, int WPC, typename Source, bool BYREGS = false>
 int launch_epa_group(const Source& src, int n, SimplexT<T>* d_simplices, T* d_distances, T* d_normals, const EpaQueue& q,
                      int sms) {
   constexpr int threads = 32 * WPC;
   constexpr int groups = threads / G;
   const size_t smem = (size_t)groups * sizeof(WT);
-  auto kern = epa_group_kernel<T, G, KV, WT, MINB, WPC, Source>;
+  void (*kern)(const Source, SimplexT<T>*, T*, T*, const int*, int*, int*, int, int) = nullptr;
+  if constexpr (BYREGS) kern = epa_group_kernel_regs<T, G, KV, WT, MINB, WPC, Source>;
+  else kern = epa_group_kernel<T, G, KV, WT, MINB, WPC, Source>;
   long long grid = 0;
   if (int rc = persistent_grid(kern, threads, smem, &grid)) return rc;
   const long long need = ((long long)n + groups - 1) / groups;
@@ -565,13 +568,13 @@ int launch_epa_group(const Source& src, int n, SimplexT<T>* d_simplices, T* d_di
 
 // Persistent EPA over a device-side queue of colliding pairs.  Default (measured on B200, profiles/r2_experiments.txt
 // sections A, E, G): bodies of up to 32 vertices take the sub-warp group kernel, G = 4 lanes per pair, followed by the
-// overflow pass -- config 3: 5.07 ms against 7.64 ms per Mi pairs for one warp per pair, config 5: 8.85 against 14.1 ms
+// overflow pass -- config 3: 4.88 ms against 7.64 ms per Mi pairs for one warp per pair, config 5: 8.40 against 14.1 ms
 // per 3.96 M pairs, 16-vertex bodies 3.43 against 6.43; larger bodies (the support scan grows, the bookkeeping does
 // not) take one warp per pair -- config 2 (64 vertices, shallow contacts): 0.30 ms against 0.34 (G = 8) and 0.48
 // (G = 4); only deep 64-vertex contacts favour G = 8 (3.04 against 3.42 ms per 512 Ki pairs).  Measured and dropped
 // (profiles/r2y5_ab_epa_svc.txt): G = 8 with four cached vertices per lane and the 1.4 KB area at 20 / 24 warps per SM
 // -- config 3 5.50 / 5.48 ms.  Development overrides: OGJK_EPA_KERNEL=warp|group (full-size area, 8 lanes)|small4|small8,
-// OGJK_EPA_SVC=<batch><defer>, OGJK_EPA_AREA=small (bodies of up to 16 vertices: 1.7 KB area instead of 1.4 KB).
+// OGJK_EPA_SVC=<batch><defer>, OGJK_EPA_AREA=small (the 1.7 KB area at 128 registers instead of the 1.4 KB ones at 96).
 template <typename T, typename Source>
 int launch_epa_queue(const Source& src, int n, int nv_hint, SimplexT<T>* d_simplices, T* d_distances, T* d_normals,
                      const EpaQueue& q) {
@@ -583,17 +586,26 @@ int launch_epa_queue(const Source& src, int n, int nv_hint, SimplexT<T>* d_simpl
   if (e) mode = !strcmp(e, "warp") ? 0 : !strcmp(e, "group") ? 1 : !strcmp(e, "small4") ? 4 : !strcmp(e, "small8") ? 8 : mode;
   constexpr int minb = sizeof(T) == 4 ? 16 : 8;
   if (mode == 4) {
-    // Two warps per CTA: eight 2-warp CTAs use the 1 KB of shared memory the system reserves per CTA eight times instead
-    // of fifteen times -- 16 warps per SM instead of 15 (config 3: 5.31 -> 5.07 ms, profiles/r2y_ab_epa_svc.txt).
-    // Bodies of up to 16 vertices (KV = 4 needs 96 registers) take the 1.4 KB area: 20 warps per SM, 3.86 -> 3.43 ms.
-    if (nv_hint <= 16) {
-      const char* area = getenv("OGJK_EPA_AREA");  // development: small | tiny
-      if constexpr (sizeof(T) == 4) {
-        if (!area || strcmp(area, "small"))
+    // Occupancy decides here (the kernel is latency-bound: issue slots 63 % busy at 16 warps per SM), and the register file
+    // only knows two useful budgets -- each scheduler owns 16 K registers, so 128 registers per thread = 4 warps per
+    // scheduler and 96 = 5; anything in between still runs 16 warps per SM (measured: profiles/r2y6_ab_epa_svc.txt).
+    //   fp32, bodies of up to 16 vertices (KV = 4 fits 96 registers): 1.4 KB area, five 4-warp CTAs = 20 warps per SM,
+    //     3.86 -> 3.43 ms per Mi pairs;
+    //   fp32, up to 32 vertices: the LEAN instantiation (per-pair state in the work area, epa_group.cuh) at 96 registers,
+    //     20 warps per SM: config 3 5.09 -> 4.88 ms, config 5 8.89 -> 8.40 ms per 3.96 M pairs (profiles/r2y7_ab_epa_svc.txt);
+    //   otherwise (fp64, OGJK_EPA_AREA=small): 1.7 KB area at 128 registers, eight 2-warp CTAs = 16 warps per SM (the 1 KB
+    //     of shared memory that the system reserves per CTA is paid 8 times instead of 15: config 3 5.31 -> 5.07 ms).
+    const char* area = getenv("OGJK_EPA_AREA");  // development: small
+    const bool small_area = area && !strcmp(area, "small");
+    if constexpr (sizeof(T) == 4) {
+      if (!small_area) {
+        if (nv_hint <= 16)
           return launch_epa_group<T, 4, 4, EpaWorkTiny<T>, 20, 4, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
+        return launch_epa_group<T, 4, 8, EpaWorkLean<T>, 96, 4, Source, true>(src, n, d_simplices, d_distances, d_normals, q, sms);
       }
-      return launch_epa_group<T, 4, 4, EpaWorkSmall<T>, minb, 2, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
     }
+    if (nv_hint <= 16)
+      return launch_epa_group<T, 4, 4, EpaWorkSmall<T>, minb, 2, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
     return launch_epa_group<T, 4, 8, EpaWorkSmall<T>, minb, 2, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
   }
   if (mode == 8) return launch_epa_group<T, 8, 8, EpaWorkSmall<T>, minb, 1, Source>(src, n, d_simplices, d_distances, d_normals, q, sms);
