@@ -109,8 +109,10 @@ struct EpaWorkLean {
   int8_t nv_in;
   uint8_t nv, hi;  // parked here while the support search has all 48 cached coordinates live
   int pair;
+  int pad[sizeof(T) == 4 ? 6 : 1];  // fp32: 1424 bytes = 356 words = 4 mod 32 -- the eight groups' areas start in disjoint bank
+                                    // quads (1400 bytes: config 5 8.39 instead of 8.32 ms, profiles/r2y8_ab_epa_svc.txt)
 };
-static_assert(sizeof(EpaWorkLean<float>) <= 1424, "five 4-warp CTAs per SM: (32 areas + 1 KB) x 5 <= 228 KB");
+static_assert(sizeof(EpaWorkLean<float>) == 1424, "five 4-warp CTAs per SM: (32 areas + 1 KB) x 5 <= 228 KB");
 
 template <int G>
 struct Grp {
