@@ -4,28 +4,31 @@
 // A.6 = the reference's scalar EPA, GJK/cpu/EPA.c:362-863), but a different machine mapping.  profiles/
 // r1c_epa_queue_cfg3.txt shows the warp-per-pair kernel issue-bound (77 % of the issue slots) with a flat profile:
 // an expansion works on ~20 live faces, a handful of dying faces, <= 18 horizon edges and 4-6 new faces, so most of
-// its ~560 warp instructions per iteration run with a fraction of the 32 lanes doing anything.  Here 8 lanes share a
-// pair and a warp carries FOUR pairs through one instruction stream:
+// its ~560 warp instructions per iteration run with a fraction of the 32 lanes doing anything.  Here G = 4 (or 8) lanes
+// share a pair and a warp carries EIGHT (four) pairs through one instruction stream:
 //   * the kernel is a persistent state machine -- a group that finishes its pair pulls the next one from the queue
-//     while the other groups of the warp keep expanding -- so the four groups stay in one loop;
+//     while the other groups of the warp keep expanding -- so all groups of a warp stay in one loop; reporting a pair
+//     and setting up the next one are batched over the groups that need it (see the loop head);
 //   * the expansion step is executed by all 32 lanes in lock step: collectives name the whole warp (each group looks
-//     at its own 8 bits / shuffles within its 8-lane segment), loops run to the maximum trip count over the four
-//     groups with per-group predicates.  (Collectives that name only the group's lanes are legal but ptxas
-//     serialises them over the distinct masks -- the first version of this kernel ran at 16 active lanes and was
-//     slower than warp-per-pair.)  Set-up and reporting, once per pair, stay group-masked and divergent;
-//   * reductions are 3-level xor butterflies on (value, lowest index);
+//     at its own G bits / shuffles within its G-lane segment), loops run to the maximum trip count over the groups
+//     with per-group predicates.  (Collectives that name only the group's lanes are legal but ptxas serialises them
+//     over the distinct masks -- the first version of this kernel ran at 16 active lanes and was slower than
+//     warp-per-pair.)  Set-up and reporting, once per pair, stay group-masked and divergent;
+//   * reductions are log2(G)-level xor butterflies on (value, lowest index);
 //   * face slot f belongs to lane f % G of the group; per-face passes run over the live slot range only;
-//   * both bodies' vertices are cached in registers (<= 64 per body: 8 per lane).
+//   * both bodies' vertices are cached in registers (KV per lane and body: bodies of up to G * KV vertices).
 // WPC warps per CTA (independent of one another: no CTA-level synchronisation).
 //
-// Work area.  With the full-size EpaWork (4.7 KB, room for the reference's 64 iterations / 128 faces) only ~11 warps
+// Work areas.  With the full-size EpaWork (4.7 KB, room for the reference's 64 iterations / 128 faces) only ~11 warps
 // fit an SM and the kernel is latency-bound (profiles/r1e_experiments.txt).  The measured distribution of EPA
-// iterations is short-tailed (config 3: mean 12.8, 99.5 % <= 24; configs 2 and 5: 99.9 % <= 25), so the default work
-// area is EpaWorkSmall: 28 vertices, 56 face slots, 48 dying-face edges -- 1.7 KB (fp32).  A pair that would exceed
-// any of the three capacities is abandoned untouched (EPA writes its outputs only when it reports) and appended to an
-// overflow queue, which the warp-per-pair kernel with the full-size work area then processes from scratch; the
-// result is therefore the same as if every pair had had the full-size area.  With 1.7 KB per pair, G = 4 lanes per
-// pair (eight pairs per warp) runs 16 warps per SM and G = 8 about 30.
+// iterations is short-tailed (config 3: mean 12.8, 99.5 % <= 24; configs 2 and 5: 99.9 % <= 25), so the areas used by
+// default are cut to that: EpaWorkSmall (28 vertices, 56 face slots, 48 dying-face edges: 1.7 KB in fp32), EpaWorkTiny
+// and EpaWorkLean (26 / 25 vertices, 1.4 KB).  A pair that would exceed any capacity of its area is abandoned
+// untouched (EPA writes its outputs only when it reports) and appended to an overflow queue, which the warp-per-pair
+// kernel with the full-size work area then processes from scratch; the result is therefore the same as if every pair
+// had had the full-size area.  The kernel is latency-bound, so what the areas buy is occupancy: G = 4 runs 16 warps
+// per SM on the 1.7 KB area (128 registers) and 20 on the 1.4 KB ones (96 registers); the launcher (ogjk_lib.cu,
+// launch_epa_queue) has the policy and the measurements.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -108,35 +108,40 @@ def test_grid_cubes_and_spheres(pkg, oracle_mod, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("kernel", ["warp", "group", "small4", "small8"])
+@pytest.mark.parametrize("kernel", ["warp", "group", "small4", "small4+small", "small8"])
 @pytest.mark.parametrize("nverts,spread", [(32, 1.0), (64, 2.0), (200, 1.5), (8, 0.5), (16, 0.3)])
 def test_epa_kernel_families_match_oracle(pkg, oracle_mod, dtype, kernel, nverts, spread):
     """every EPA kernel family forced through OGJK_EPA_KERNEL (needs >= 8192 pairs to leave the tiny-batch kernel):
-    warp per pair; sub-warp group with the full-size work area; sub-warp groups of 4 / 8 lanes with the SMALL work
-    area + overflow pass -- deep overlaps (spread 0.3 .. 1) send the long-tailed pairs through the overflow queue,
-    200-vertex bodies run the uncached support path"""
+    warp per pair; sub-warp group with the full-size work area; sub-warp groups of 4 / 8 lanes with the small work
+    areas + overflow pass -- deep overlaps (spread 0.3 .. 1) send the long-tailed pairs through the overflow queue.
+    `small4` in fp32 is the default policy's pair of 96-register instantiations (1.4 KB area up to 16 vertices, the lean
+    area above: bodies of more than 32 vertices all take the overflow pass there); `small4+small` (OGJK_EPA_AREA=small) and
+    fp64 run the 1.7 KB area, where 200-vertex bodies take the uncached support path of the group kernel"""
     import os
     n = 30000 if nverts <= 64 else 9000
     a, b = pkg.workloads.random_pairs(n, nverts, spread, seed=123, dtype=dtype)
     eng = pkg.Engine(dtype)
     bd1, _k1 = pkg.make_polytopes(a)
     bd2, _k2 = pkg.make_polytopes(b)
-    saved = os.environ.get("OGJK_EPA_KERNEL")
-    os.environ["OGJK_EPA_KERNEL"] = kernel
+    saved = {k: os.environ.get(k) for k in ("OGJK_EPA_KERNEL", "OGJK_EPA_AREA")}
+    os.environ["OGJK_EPA_KERNEL"] = kernel.split("+")[0]
+    if "+" in kernel:
+        os.environ["OGJK_EPA_AREA"] = kernel.split("+")[1]
     try:
         got = eng.compute_gjk_epa(bd1, bd2)
     finally:
-        if saved is None:
-            os.environ.pop("OGJK_EPA_KERNEL", None)
-        else:
-            os.environ["OGJK_EPA_KERNEL"] = saved
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     orc = oracle_mod.Oracle("port", dtype)
     s, d = orc.gjk(a, b, nthreads=8)
     _compare(dtype, got, orc.epa(a, b, s, d, nthreads=8))
 
 
 def test_small_work_area_overflow_is_exercised(pkg, oracle_mod):
-    """the workload above really has pairs beyond the small work area's 24 iterations (so the overflow pass ran)"""
+    """the workload above really has pairs beyond the small work areas' 22 .. 24 iterations (so the overflow pass ran)"""
     a, b = pkg.workloads.random_pairs(30000, 32, 1.0, seed=123, dtype=np.float32)
     orc = oracle_mod.Oracle("port", np.float32)
     s, d = orc.gjk(a, b, nthreads=8)
