@@ -266,9 +266,10 @@ OGJK_D int grp_closest_face(const Grp<G>& g, const WT& W, int nj, int trips, T& 
 }
 
 // KV: vertices per lane of each body cached in registers (bodies of up to G * KV vertices; larger ones are read from
-// global memory on every support search).  WT: work area type (EpaWork<T> or EpaWorkSmall<T>).  counters: [0] queued
-// pairs, [1] ticket, [2] overflow count (small work area only: pairs appended to `overflow`).  MINB: resident warps per SM
-// the registers are budgeted for (the launch bound is MINB / WPC CTAs of WPC warps).
+// global memory on every support search -- or, in the lean instantiation, handed to the overflow queue).  WT: work area
+// type (EpaWork, EpaWorkSmall, EpaWorkTiny, EpaWorkLean; WT::kLean selects the register-lean variant of the loop).
+// counters: [0] queued pairs, [1] ticket, [2] overflow count (small work areas only: pairs appended to `overflow`).
+// svc_batch / svc_defer: batching of the per-pair service code, see the loop head.
 template <typename T, int G, int KV, typename WT, typename Source>
 OGJK_D void epa_group_body(const Source& src, SimplexT<T>* __restrict__ simplices, T* __restrict__ distances,
                            T* __restrict__ normals, const int* __restrict__ queue, int* __restrict__ counters,
